@@ -1,0 +1,329 @@
+// CUDA-core kernels of the spectral front-end (sm_100a):
+//   fe_fft_kernel    staging (reflect / repeat-pad / pre-emphasis) -> framing+window -> real FFT ->
+//                    power -> [filterbank] -> tile store (+ per-group maximum for top_db)
+//   fe_tail_kernel   log / dB + top_db clamp -> DCT-II -> delta / delta-delta -> one coalesced store
+//   fe_cmvn_kernel   optional per-utterance mean / variance normalisation
+//   fe_deltas_kernel stand-alone ComputeDeltas
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "fe_fft.cuh"
+#include "fe_tail.cuh"
+#include "fe_kernels.h"
+
+namespace {
+
+constexpr int kFftWarps = 8;
+constexpr int kFftThreads = kFftWarps * 32;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fe_fft_kernel
+//   grid.x = rows * tiles_per_row ; one CTA = `ft` consecutive frames of one row
+//   MODE 0: write the power spectrum  out[row][k][t]
+//   MODE 1: write filterbank energies ws[row_local][f][t] and atomicMax the group maximum
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kFftThreads) fe_fft_kernel(fe_fft_args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n_fft = a.n_fft, nh = n_fft >> 1, n_freq = nh + 1, hop = a.hop;
+  const int ft = a.ft;
+  const int seg = (ft - 1) * hop + n_fft;  // staged samples
+
+  // carve shared memory
+  float* s_stage = reinterpret_cast<float*>(smem_raw);
+  size_t off = ((size_t)seg * 4 + 15) & ~(size_t)15;
+  float* s_win = reinterpret_cast<float*>(smem_raw + off);
+  off += (size_t)n_fft * 4;
+  fe_c2* s_tw = reinterpret_cast<fe_c2*>(smem_raw + off);
+  off += (size_t)nh * 8;
+  fe_c2* s_rtw = reinterpret_cast<fe_c2*>(smem_raw + off);
+  off += (((size_t)(nh / 2 + 1) * 8) + 15) & ~(size_t)15;
+  fe_c2* s_buf = reinterpret_cast<fe_c2*>(smem_raw + off);  // [warps][2][nh+1]
+  off += (size_t)kFftWarps * 2 * (nh + 1) * 8;
+  float* s_tile = reinterpret_cast<float*>(smem_raw + off);  // MODE0: [n_freq][ft+1]; MODE1: [n_filter][ft+1]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row_local = blockIdx.x / a.tiles_per_row;
+  const int tile = blockIdx.x - (int)(row_local * a.tiles_per_row);
+  const int64_t row = a.row_base + row_local;
+  const int t0 = tile * ft;
+  const int nf_here = min(ft, a.n_frames - t0);
+
+  const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
+  const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
+
+  // ---- constants -> shared --------------------------------------------------------------------
+  {
+    const float* gw = reinterpret_cast<const float*>(blob + h->off_window);
+    for (int i = tid; i < n_fft; i += kFftThreads) s_win[i] = gw[i];
+    const fe_c2* gt = reinterpret_cast<const fe_c2*>(blob + h->off_twiddle);
+    for (int i = tid; i < nh; i += kFftThreads) s_tw[i] = gt[i];
+    const fe_c2* gr = reinterpret_cast<const fe_c2*>(blob + h->off_rtwiddle);
+    for (int i = tid; i <= nh / 2; i += kFftThreads) s_rtw[i] = gr[i];
+  }
+
+  // ---- stage the waveform segment -------------------------------------------------------------
+  // Padded position pp = t0*hop + i  (reflect padding by n_fft/2, torch.stft center=True); the
+  // T-sample signal itself is the clip repeat-padded / truncated to T (pad(), maze5.py:280-285).
+  {
+    const float* src;
+    int clip_len;  // T < 2^31 is checked on the host
+    if (a.offsets) {
+      src = a.wave + a.offsets[row];
+      clip_len = a.lengths[row];
+    } else {
+      src = a.wave + row * a.T;
+      clip_len = (int)a.T;
+    }
+    const int seg_here = (nf_here - 1) * hop + n_fft;
+    fe_stage_load(tid, kFftThreads, src, clip_len, (int)a.T, n_fft, t0 * hop, seg_here, a.preemph, s_stage);
+  }
+  __syncthreads();
+
+  // ---- per-warp FFTs --------------------------------------------------------------------------
+  fe_c2* buf0 = s_buf + (size_t)warp * 2 * (nh + 1);
+  fe_c2* buf1 = buf0 + (nh + 1);
+  const int tile_stride = ft + 1;
+  const int32_t* bstart = reinterpret_cast<const int32_t*>(blob + h->off_band_start);
+  const int32_t* blen = reinterpret_cast<const int32_t*>(blob + h->off_band_len);
+  const int32_t* bwoff = reinterpret_cast<const int32_t*>(blob + h->off_band_woff);
+  const float* bw = reinterpret_cast<const float*>(blob + h->off_band_w);
+
+  for (int fl = warp; fl < nf_here; fl += kFftWarps) {
+    const float* frame = s_stage + (size_t)fl * hop;
+    fe_c2* in = buf0;
+    fe_c2* out = buf1;
+    fe_fft_stage_first(lane, frame, s_win, out, nh, a.radix2_first != 0);
+    __syncwarp();
+    int ns = a.radix2_first ? 2 : 4;
+    while (ns < nh) {
+      fe_c2* t = in; in = out; out = t;
+      fe_fft_stage4(lane, in, out, s_tw, nh, ns);
+      __syncwarp();
+      ns <<= 2;
+    }
+    // `out` holds Z; write the power into the other buffer (nh+1 floats fit in nh+1 complex slots)
+    float* pw = reinterpret_cast<float*>(in);
+    fe_fft_power(lane, out, s_rtw, pw, nh);
+    __syncwarp();
+    if (MODE == 0) {
+      for (int k = lane; k < n_freq; k += 32) s_tile[(size_t)k * tile_stride + fl] = pw[k];
+    } else {
+      fe_fbank_apply(lane, pw, bstart, blen, bwoff, bw, a.n_filter, s_tile + fl, tile_stride);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- coalesced tile store -------------------------------------------------------------------
+  const int n_ch = (MODE == 0) ? n_freq : a.n_filter;
+  float* dst = a.out + ((size_t)row_local * n_ch) * a.n_frames + t0;
+  float vmax = 0.0f;
+  // thread -> (channel, frame) with frame fastest so that consecutive lanes write consecutive t
+  const int per_ch = nf_here;
+  const int total = n_ch * per_ch;
+  for (int i = tid; i < total; i += kFftThreads) {
+    const int c = i / per_ch, t = i - c * per_ch;
+    const float v = s_tile[(size_t)c * tile_stride + t];
+    dst[(size_t)c * a.n_frames + t] = v;
+    vmax = fmaxf(vmax, v);
+  }
+  if (MODE == 1 && a.group_max) {
+    vmax = warp_max(vmax);
+    __shared__ float s_red[kFftWarps];
+    if (lane == 0) s_red[warp] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+      float m = s_red[0];
+#pragma unroll
+      for (int w = 1; w < kFftWarps; ++w) m = fmaxf(m, s_red[w]);
+      // energies are >= 0, so the unsigned ordering of the bit patterns is the float ordering
+      atomicMax(a.group_max + row / a.top_db_group, __float_as_uint(m));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fe_tail_kernel : grid (tiles, rows_in_chunk), block kTailThreads
+// ------------------------------------------------------------------------------------------------
+constexpr int kTailThreads = 128;
+
+__global__ void __launch_bounds__(kTailThreads) fe_tail_kernel(fe_tail_args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tt = a.tt, halo = a.halo, w = tt + 2 * halo;
+  const int nfil = a.n_filter, ncoef = a.n_coef;
+  const int nc = ncoef > 0 ? ncoef : nfil;  // channels per block of the output
+  float* s_e = reinterpret_cast<float*>(smem_raw);  // [nfil][w]   (log) energies
+  float* s_c = s_e + (size_t)nfil * w;              // [nc][w]     coefficients (aliases s_e when no DCT)
+  if (ncoef == 0) s_c = s_e;
+  float* s_d = s_c + (size_t)nc * w;                // [nc][w]     deltas
+  float* s_dct = s_d + (a.deltas > 0 ? (size_t)nc * w : 0);  // [nfil][ncoef]
+
+  const int tid = threadIdx.x;
+  const int64_t row_local = blockIdx.y;
+  const int64_t row = a.row_base + row_local;
+  const int t0 = blockIdx.x * tt;
+  const int nF = a.n_frames;
+  const int tv0 = t0 - halo;  // virtual frame index of tile position 0
+
+  const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
+  const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
+  if (ncoef > 0) {
+    const float* gd = reinterpret_cast<const float*>(blob + h->off_dct);
+    for (int i = tid; i < nfil * ncoef; i += kTailThreads) s_dct[i] = gd[i];
+  }
+
+  float floor_db = -INFINITY;
+  if (a.log_mode == B200FE_LOG_DB && a.top_db >= 0.0f) {
+    const float gmax = __uint_as_float(a.group_max[row / a.top_db_group]);
+    floor_db = 10.0f * log10f(fmaxf(gmax, 1e-10f)) - a.top_db;
+  }
+  const float* src = a.energies + (size_t)row_local * nfil * nF;
+  fe_tail_load(tid, kTailThreads, src, nfil, nF, w, tv0, a.log_mode, floor_db, s_e);
+  __syncthreads();
+  if (ncoef > 0) {
+    fe_tail_dct(tid, kTailThreads, s_e, s_dct, nfil, ncoef, w, s_c);
+    __syncthreads();
+  }
+  const int n = (a.delta_win - 1) / 2;
+  float* out_row = a.out + (size_t)row * a.n_out * nF;
+  const int nt_here = min(tt, nF - t0);
+  if (a.deltas >= 1) {
+    fe_tail_delta(tid, kTailThreads, s_c, nc, w, n, tv0, nF, s_d);
+    __syncthreads();
+  }
+  fe_tail_store(tid, kTailThreads, s_c, s_d, nc, w, n, halo, t0, nt_here, nF, a.deltas, out_row);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fe_cmvn_kernel : one warp per (row, channel); in place
+// ------------------------------------------------------------------------------------------------
+__global__ void fe_cmvn_kernel(float* out, int64_t n_series, int n_frames, float eps) {
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_series) return;
+  const int lane = threadIdx.x & 31;
+  float* p = out + s * n_frames;
+  float sum = 0.0f;
+  for (int t = lane; t < n_frames; t += 32) sum += p[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)n_frames;
+  float var = 0.0f;
+  for (int t = lane; t < n_frames; t += 32) {
+    const float d = p[t] - mean;
+    var = fmaf(d, d, var);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float inv = 1.0f / (sqrtf(var / (float)n_frames) + eps);
+  for (int t = lane; t < n_frames; t += 32) p[t] = (p[t] - mean) * inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fe_deltas_kernel : stand-alone ComputeDeltas on [rows][T]
+// ------------------------------------------------------------------------------------------------
+__global__ void fe_deltas_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows,
+                                 int64_t T, int n, float denom) {
+  const int64_t row = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows || t >= T) return;
+  const float* p = in + row * T;
+  float acc = 0.0f;
+  for (int m = -n; m <= n; ++m) {
+    int64_t u = t + m;
+    u = u < 0 ? 0 : (u >= T ? T - 1 : u);
+    acc += (float)m * __ldg(p + u);
+  }
+  out[row * T + t] = acc / denom;
+}
+
+cudaError_t set_smem(const void* fn, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace
+
+size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch) {
+  const int nh = n_fft / 2;
+  size_t seg = (size_t)(ft - 1) * hop + n_fft;
+  size_t b = (seg * 4 + 15) & ~(size_t)15;
+  b += (size_t)n_fft * 4 + (size_t)nh * 8 + ((((size_t)(nh / 2 + 1)) * 8 + 15) & ~(size_t)15);
+  b += (size_t)kFftWarps * 2 * (nh + 1) * 8;
+  b += (size_t)n_ch * (ft + 1) * 4;
+  return b;
+}
+
+cudaError_t fe_launch_fft(const fe_fft_args& a, int mode, int64_t rows, cudaStream_t stream) {
+  const int n_ch = mode == 0 ? a.n_fft / 2 + 1 : a.n_filter;
+  const size_t smem = fe_fft_smem_bytes(a.n_fft, a.hop, a.ft, n_ch);
+  const int64_t grid = rows * a.tiles_per_row;
+  if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  cudaError_t e;
+  if (mode == 0) {
+    e = set_smem((const void*)fe_fft_kernel<0>, smem);
+    if (e != cudaSuccess) return e;
+    fe_fft_kernel<0><<<(unsigned)grid, kFftThreads, smem, stream>>>(a);
+  } else {
+    e = set_smem((const void*)fe_fft_kernel<1>, smem);
+    if (e != cudaSuccess) return e;
+    fe_fft_kernel<1><<<(unsigned)grid, kFftThreads, smem, stream>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+size_t fe_tail_smem_bytes(const fe_tail_args& a) {
+  const int w = a.tt + 2 * a.halo;
+  const int nc = a.n_coef > 0 ? a.n_coef : a.n_filter;
+  size_t fl = (size_t)a.n_filter * w;
+  if (a.n_coef > 0) fl += (size_t)nc * w;
+  if (a.deltas > 0) fl += (size_t)nc * w;
+  fl += (size_t)a.n_filter * a.n_coef;
+  return fl * 4;
+}
+
+cudaError_t fe_launch_tail(const fe_tail_args& a, int64_t rows, cudaStream_t stream) {
+  const size_t smem = fe_tail_smem_bytes(a);
+  cudaError_t e = set_smem((const void*)fe_tail_kernel, smem);
+  if (e != cudaSuccess) return e;
+  const int tiles = (a.n_frames + a.tt - 1) / a.tt;
+  // grid.y is limited to 65535 rows per launch
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+    fe_tail_args b = a;
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    b.row_base = a.row_base + r0;
+    b.energies = a.energies + (size_t)r0 * a.n_filter * a.n_frames;
+    dim3 grid((unsigned)tiles, (unsigned)nr);
+    fe_tail_kernel<<<grid, kTailThreads, smem, stream>>>(b);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t fe_launch_cmvn(float* out, int64_t n_series, int n_frames, cudaStream_t stream) {
+  const int warps = 8;
+  const int64_t grid = (n_series + warps - 1) / warps;
+  fe_cmvn_kernel<<<(unsigned)grid, warps * 32, 0, stream>>>(out, n_series, n_frames, 1e-5f);
+  return cudaGetLastError();
+}
+
+cudaError_t fe_launch_deltas(const float* in, float* out, int64_t rows, int64_t T, int win,
+                             cudaStream_t stream) {
+  const int n = (win - 1) / 2;
+  const float denom = (float)(n * (n + 1) * (2 * n + 1)) / 3.0f;
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    dim3 grid((unsigned)((T + 255) / 256), (unsigned)nr);
+    fe_deltas_kernel<<<grid, 256, 0, stream>>>(in + r0 * T, out + r0 * T, nr, T, n, denom);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}

@@ -1,0 +1,43 @@
+// Launch interface of the CUDA-core kernels (fe_kernels.cu) and the tcgen05 kernel (fe_gemm.cu).
+#ifndef FE_KERNELS_H_
+#define FE_KERNELS_H_
+#include <cuda_runtime.h>
+#include "fe_common.h"
+
+struct fe_fft_args {
+  const float* wave;        // dense [R][T] or flat ragged clips
+  const int64_t* offsets;   // ragged: start of each row's clip (floats), else NULL
+  const int32_t* lengths;   // ragged: clip lengths, else NULL
+  const void* tables;       // device blob
+  float* out;               // MODE 0: [rows][n_freq][n_frames]; MODE 1: energies [rows_in_launch][n_filter][n_frames]
+  unsigned int* group_max;  // per top_db group maximum energy (float bits), NULL when not needed
+  int64_t T;
+  int64_t row_base;         // absolute index of the launch's first row
+  int32_t n_fft, hop, n_frames, n_filter;
+  int32_t ft;               // frames per CTA
+  int32_t tiles_per_row;
+  int32_t radix2_first;     // log2(n_fft/2) odd
+  int32_t top_db_group;
+  float preemph;
+};
+
+struct fe_tail_args {
+  const float* energies;    // [rows_in_launch][n_filter][n_frames]
+  const unsigned int* group_max;
+  const void* tables;
+  float* out;               // [R][n_out][n_frames] (absolute rows)
+  int64_t row_base;
+  int32_t n_frames, n_filter, n_coef, n_out;
+  int32_t log_mode, deltas, delta_win, top_db_group;
+  int32_t tt, halo;         // frames per CTA, halo frames each side (= deltas * (delta_win-1)/2)
+  float top_db;
+};
+
+size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch);
+cudaError_t fe_launch_fft(const fe_fft_args& a, int mode, int64_t rows, cudaStream_t stream);
+size_t fe_tail_smem_bytes(const fe_tail_args& a);
+cudaError_t fe_launch_tail(const fe_tail_args& a, int64_t rows, cudaStream_t stream);
+cudaError_t fe_launch_cmvn(float* out, int64_t n_series, int n_frames, cudaStream_t stream);
+cudaError_t fe_launch_deltas(const float* in, float* out, int64_t rows, int64_t T, int win,
+                             cudaStream_t stream);
+#endif

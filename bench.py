@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Headline benchmark: utterances/s of the fused LFCC + delta + delta-delta front-end (BASELINE.json
+config 2: batch 4096 synthetic 64600-sample 16 kHz utterances per GPU), with the HBM roofline of the
+dominant kernel, the same path end-to-end through host buffers, and the reference CPU path
+(torchaudio on the host's cores) timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (rank 0 only)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+UTT_LEN = 64600
+SEED = 1234  # the reference's default seed (maze5.py:449)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "lfcc": dict(
+        name="LFCC(20)+delta+delta-delta, n_fft=512 win=320 hop=160, batch 4096 x 64600 samples (BASELINE config 2)",
+        batch=4096, n_out=60, n_frames=404,
+        bytes_per_utt=UTT_LEN * 4 + 60 * 404 * 4,  # 355,360 B: waveform read once + features written once
+    ),
+    # BASELINE.json configs[2] (not the headline; selectable for measurements)
+    "mel": dict(
+        name="80-bin log-mel (dB), n_fft=1024 hop=256, batch 8192 x 64600 samples (BASELINE config 3)",
+        batch=8192, n_out=80, n_frames=253,
+        bytes_per_utt=UTT_LEN * 4 + 80 * 253 * 4,  # 339,360 B
+    ),
+}
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_modules(workload, variant):
+    import b200_frontend as fe
+    if workload == "lfcc":
+        return fe.LFCCDelta(16000, n_filter=20, n_lfcc=20, speckwargs=dict(n_fft=512, win_length=320, hop_length=160),
+                            variant=variant)
+    return fe.MelSpectrogram(16000, n_fft=1024, hop_length=256, n_mels=80, log="db", variant=variant)
+
+
+def make_reference(workload):
+    from oracle.torchaudio_ref import LFCCDeltaRef, LogMelRef
+    return LFCCDeltaRef() if workload == "lfcc" else LogMelRef()
+
+
+def cpu_reference_throughput(workload, budget_s, batch=64, max_batches=10_000, threads=None):
+    """The reference CPU path (torchaudio transforms, oracle/torchaudio_ref.py) on the host cores,
+    B=64 chunks of S1 noise as BASELINE.md section 3 prescribes; returns (utt/s, threads, n_utts)."""
+    import torch
+    from oracle import synth
+    if threads:
+        torch.set_num_threads(threads)
+    ref = make_reference(workload)
+    x = torch.from_numpy(synth.s1_noise(batch, UTT_LEN, seed=SEED))
+    ref(x)  # warm-up
+    ref(x)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        ref(x)
+        n += batch
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= max_batches * batch:
+            break
+    return n / el, torch.get_num_threads(), n
+
+
+def run_reference_arm(args):
+    """Reference arm: the reference's own CPU implementation of the path (torchaudio transforms, all
+    host threads) on the same workload; each step is a bounded sample (B=64 chunks for a few seconds)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    w = WORKLOADS[args.workload]
+    per_step_budget = max(1.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(args.warmup):
+        cpu_reference_throughput(args.workload, min(1.0, per_step_budget), threads=cores)
+    total_n, total_t, threads = 0, 0.0, cores
+    for _ in range(args.steps):
+        thr, threads, n = cpu_reference_throughput(args.workload, per_step_budget, threads=cores)
+        total_n += n
+        total_t += n / thr
+    value = total_n / total_t
+    line = {
+        "impl": "reference", "metric": "utterances/sec (4 s, 16 kHz) LFCC+delta+delta-delta front-end"
+        if args.workload == "lfcc" else "utterances/sec (4 s, 16 kHz) 80-bin log-mel front-end",
+        "value": value, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * total_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"],
+                   "sample": f"each step: B=64 chunks of S1 noise for ~{per_step_budget:.0f} s on {threads} host threads"},
+        "cpu_baseline": {"value": value, "unit": "utterances/s", "cores": threads, "kind": "reference",
+                         "sample": f"torchaudio {args.workload} path, {total_n} utterances in B=64 chunks, {threads} threads"},
+        "e2e": {"value": value, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="lfcc", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default="auto", choices=["auto", "fft", "dft_gemm"])
+    ap.add_argument("--batch", type=int, default=0, help="override utterances per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the front-end has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    W = dict(WORKLOADS[args.workload])
+    B = args.batch or W["batch"]
+    K, WU = args.steps, max(args.warmup, 3)
+    mod = make_modules(args.workload, args.variant)
+    eng = mod.engine
+    variant = eng.resolved_variant()
+
+    # ---- synthetic inputs resident in HBM: set S1, seed 1234 (+rank), 3 rotating buffer sets > L2 ----
+    n_sets = 3
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED + rank)
+    waves = [(0.1 * torch.randn(B, UTT_LEN, device=dev, generator=gen)).clamp_(-1.0, 1.0) for _ in range(n_sets)]
+    outs = [torch.empty(B, W["n_out"], W["n_frames"], device=dev) for _ in range(n_sets)]
+    energies = torch.empty(B, eng.params.n_filter, W["n_frames"], device=dev)
+
+    def step(i):
+        eng.features(waves[i % n_sets], out=outs[i % n_sets])
+
+    for i in range(WU):
+        step(i)
+    launches_per_step = eng.last_launch_count()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device events on the launching stream, barrier + sync both sides ----
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for i in range(K):
+            step(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        # dominant kernel alone (same launches as inside the step), for the roofline line
+        for i in range(2):
+            eng.fbank_energies(waves[i % n_sets], out=energies)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(K):
+            eng.fbank_energies(waves[i % n_sets], out=energies)
+        k1.record()
+        torch.cuda.synchronize()
+        dom_launches = eng.last_launch_count()
+        dom_ms = k0.elapsed_time(k1) / K
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / K
+    value = world * B * K / (elapsed_ms / 1000.0)
+
+    # ---- end to end through host buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        Be = B
+        xh = torch.empty(Be, UTT_LEN, dtype=torch.float32, pin_memory=True)
+        xh.copy_(waves[0][:Be])
+        oh = torch.empty(Be, W["n_out"], W["n_frames"], dtype=torch.float32, pin_memory=True)
+        ke = max(2, min(K, 5))
+        mod.forward_host(xh, oh, chunk_rows=256, n_streams=3)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            mod.forward_host(xh, oh, chunk_rows=256, n_streams=3)  # blocks until the features are on the host
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * Be * ke / float(te.item()), "unit": "utterances/s",
+               "h2d_bytes_per_step": Be * UTT_LEN * 4, "d2h_bytes_per_step": Be * W["n_out"] * W["n_frames"] * 4,
+               "steps": ke, "api": "LFCCDelta.forward_host -> b200fe_features_forward_host (pinned host buffers, 3 streams)"}
+        del xh, oh
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = read_peaks()
+    alg_bytes_step = B * W["bytes_per_utt"]
+    dom_gbs = alg_bytes_step / (dom_ms / 1000.0) / 1e9
+    step_gbs = alg_bytes_step / (ms_per_step / 1000.0) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+        "peak_source": peak_src,
+        "kernel": ("fe_gemm_kernel" if variant == "dft_gemm" else "fe_fft_kernel<1>"),
+        "kernel_ms_per_step": dom_ms, "kernel_launches_per_step": int(dom_launches),
+        "kernel_share_of_step": dom_ms / ms_per_step,
+        "algorithmic_bytes_per_utt": W["bytes_per_utt"],
+        "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak,
+    }
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        thr, threads, n = cpu_reference_throughput(args.workload, args.cpu_budget)
+        cpu_baseline = {"value": thr, "unit": "utterances/s", "cores": threads, "kind": "reference",
+                        "sample": f"torchaudio {args.workload} path on host, {n} S1 utterances in B=64 chunks, "
+                                  f"{threads} threads ({os.cpu_count()} logical cores)"}
+    line = {
+        "metric": "utterances/sec (4 s, 16 kHz) LFCC+delta+delta-delta front-end" if args.workload == "lfcc"
+        else "utterances/sec (4 s, 16 kHz) 80-bin log-mel front-end",
+        "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": WU,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if variant == "fft" else "f32 (split-fp16 tensor-core DFT, fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": W["name"], "batch_per_gpu": B, "variant": variant,
+                   "l2": f"inputs/outputs rotate over {n_sets} buffer sets of {alg_bytes_step / 1e9:.2f} GB (> 126 MB L2)",
+                   "parallelism": f"dp{world} (utterance shards, no collective on the feature path)"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": int(launches_per_step) * K, "clocks": clocks.summary(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,289 @@
+"""Parity of the CUDA path (called through the C-ABI via the drop-in modules) against the committed
+golden vectors, the reference CPU path (torchaudio, live) and the oracle restatement.  Needs a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (FULL_TONAL, LFCC_CFG, MEL_CFG, SHORT_TONAL, TOL, TOL_TONAL, TOL_TONAL_MEL, assert_feat_close,
+                     assert_rows_close, feat_err, golden, golden_full_rows, golden_short_rows)
+from oracle import frontend_oracle as O
+from oracle import synth
+from oracle.torchaudio_ref import LFCCDeltaRef, LogMelRef
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = ["fft", "dft_gemm"]
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev())
+
+
+def _variant_or_skip(fe, variant, **kw):
+    try:
+        m = fe.LFCCDelta(**LFCC_CFG, variant=variant, **kw)
+        m.engine.resolved_variant()
+        return m
+    except NotImplementedError:
+        pytest.skip(f"variant {variant} not available in this build")
+
+
+def test_native_library_is_the_path_that_runs(fe):
+    lib = fe._lib.load()
+    assert lib.b200fe_version() == 1
+    m = fe.LFCCDelta(**LFCC_CFG)
+    out = m(cuda(synth.s1_noise(2)))
+    torch.cuda.synchronize()
+    assert m.engine.last_launch_count() >= 2  # our kernels were launched, nothing else computes this
+    assert out.shape == (2, 60, 404) and out.is_contiguous() and out.dtype == torch.float32
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_lfcc_golden_full(fe, variant):
+    m = _variant_or_skip(fe, variant)
+    out = m(cuda(golden_full_rows()).unsqueeze(1)).squeeze(1).cpu().numpy()
+    assert_rows_close(out, golden()["lfcc_dd_full"], FULL_TONAL, f"{variant} vs golden lfcc_dd_full")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_lfcc_golden_short(fe, variant):
+    m = _variant_or_skip(fe, variant)
+    out = m(cuda(golden_short_rows())).cpu().numpy()
+    assert_rows_close(out, golden()["lfcc_dd_short"], SHORT_TONAL, f"{variant} vs golden lfcc_dd_short")
+
+
+def test_lfcc_variants_golden(fe):
+    g = golden()
+    x = cuda(golden_short_rows())
+    out = fe.LFCC(**LFCC_CFG, log_lf=True)(x).cpu().numpy()
+    assert_rows_close(out, g["lfcc_loglf_short"], SHORT_TONAL, "log_lf")
+    out = fe.LFCC(16000, n_filter=128, n_lfcc=40, deltas=1, speckwargs=LFCC_CFG["speckwargs"])(x).cpu().numpy()
+    assert_rows_close(out, g["lfcc_default128_short"], SHORT_TONAL, "n_filter=128 n_lfcc=40")
+    out = fe.LFCCDelta(**LFCC_CFG, preemphasis=0.97)(x).cpu().numpy()
+    assert_rows_close(out, g["lfcc_preemph_short"], SHORT_TONAL, "preemphasis")
+
+
+def test_mel_golden(fe):
+    g = golden()
+    out = fe.MelSpectrogram(**MEL_CFG, log="db")(cuda(golden_full_rows()[:2])).cpu().numpy()
+    assert_rows_close(out, g["mel_db_full"], (1,), "mel db", TOL_TONAL_MEL)
+    x = cuda(golden_short_rows())
+    out = fe.MelSpectrogram(**MEL_CFG)(x).cpu().numpy()
+    ref = g["mel_power_short"]
+    assert np.abs(out - ref).max() <= 2e-5 * ref.max()
+    out = fe.MelSpectrogram(**MEL_CFG, log="log")(x).cpu().numpy()
+    assert_rows_close(out, g["mel_log_short"], SHORT_TONAL, "mel log", TOL_TONAL_MEL)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_config1_against_reference_cpu_path(fe, variant):
+    """BASELINE config 1 (64 S1 utterances) — CUDA path vs torchaudio on the host, same inputs."""
+    m = _variant_or_skip(fe, variant)
+    x = synth.s1_noise(64)
+    ref = LFCCDeltaRef()(torch.from_numpy(x)).numpy()
+    out = m(cuda(x).unsqueeze(1))
+    assert out.shape == (64, 1, 60, 404)
+    assert_feat_close(out.squeeze(1).cpu().numpy(), ref, TOL, f"{variant} vs torchaudio, config 1")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_as_close_to_float64_truth_as_the_reference(fe, variant):
+    """On tonal / edge inputs both fp32 implementations are compared with a float64 evaluation:
+    ours must not be further from the truth than torchaudio is (plus a small slack)."""
+    m = _variant_or_skip(fe, variant)
+    x = np.concatenate([synth.s2_speechlike(3), synth.s3_edge()], 0)
+    ref = LFCCDeltaRef()(torch.from_numpy(x)).numpy()
+    g64 = O.lfcc(x.astype(np.float64), deltas=2, dtype=np.float64)
+    out = m(cuda(x)).cpu().numpy()
+    e_ours, e_ref = feat_err(out, g64), feat_err(ref, g64)
+    assert (e_ours <= 2.0 * e_ref + 2e-5).all(), (e_ours, e_ref)
+    assert (feat_err(out, ref) <= TOL_TONAL).all()
+
+
+def test_spectrogram_stage(fe):
+    import torchaudio.transforms as T
+    x = synth.s1_noise(3, 20000)
+    ref = T.Spectrogram(n_fft=512, win_length=320, hop_length=160)(torch.from_numpy(x)).numpy()
+    out = fe.Spectrogram(n_fft=512, win_length=320, hop_length=160)(cuda(x)).cpu().numpy()
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 1e-5 * ref.max()   # stage tolerance: rtol 1e-5 of the peak
+    x1 = cuda(x[0])
+    assert fe.Spectrogram(n_fft=512, win_length=320, hop_length=160)(x1).shape == (257, 126)
+
+
+@pytest.mark.parametrize("n_fft,win,hop", [(64, 64, 16), (128, 100, 37), (256, 200, 80), (1024, 1024, 256),
+                                           (2048, 1200, 512), (4096, 4096, 1024)])
+def test_spectrogram_sizes(fe, n_fft, win, hop):
+    T_ = 3 * n_fft + 77
+    x = synth.s1_noise(5, T_, seed=n_fft)
+    ref = O.power_spectrogram(x.astype(np.float64), n_fft, win, hop, window=O.hann_window(win, np.float64))
+    out = fe.Spectrogram(n_fft=n_fft, win_length=win, hop_length=hop)(cuda(x)).cpu().numpy()
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 2e-6 * ref.max()
+
+
+def test_compute_deltas_module(fe):
+    import torchaudio.functional as AF
+    rs = np.random.RandomState(2)
+    c = rs.randn(4, 20, 404).astype(np.float32)
+    for win in (3, 5, 9):
+        ref = AF.compute_deltas(torch.from_numpy(c), win_length=win).numpy()
+        out = fe.ComputeDeltas(win_length=win)(cuda(c)).cpu().numpy()
+        assert np.abs(out - ref).max() < 2e-6
+    tiny = rs.randn(2, 3).astype(np.float32)   # T shorter than the window
+    ref = AF.compute_deltas(torch.from_numpy(tiny)).numpy()
+    assert np.abs(fe.ComputeDeltas()(cuda(tiny)).cpu().numpy() - ref).max() < 1e-6
+
+
+def test_input_ranks_and_layout(fe):
+    m = fe.LFCCDelta(**LFCC_CFG)
+    x = cuda(synth.s1_noise(4))
+    a = m(x)
+    b = m(x.unsqueeze(1))
+    c = m(x[0])
+    d = m(x.reshape(2, 2, -1))
+    assert a.shape == (4, 60, 404) and b.shape == (4, 1, 60, 404) and c.shape == (60, 404) and d.shape == (2, 2, 60, 404)
+    assert torch.equal(a, b.squeeze(1)) and torch.equal(a[0], c) and torch.equal(a, d.reshape(4, 60, 404))
+    assert all(t.is_contiguous() for t in (a, b, c, d))
+    # a non-contiguous view is accepted (copied), like torchaudio accepts it
+    xt = cuda(synth.s1_noise(4)).t().contiguous().t()
+    assert torch.equal(m(xt), a)
+
+
+def test_batch_independence_and_permutation(fe):
+    """Utterance i's features do not depend on its batch mates (per-utterance top_db)."""
+    m = fe.LFCCDelta(**LFCC_CFG)
+    x = np.concatenate([synth.s1_noise(3), synth.s3_edge()[4:6]], 0)
+    full = m(cuda(x))
+    for i in range(x.shape[0]):
+        assert torch.equal(m(cuda(x[i:i + 1]))[0], full[i])
+    perm = np.array([4, 2, 0, 3, 1])
+    assert torch.equal(m(cuda(x[perm])), full[perm])
+
+
+def test_top_db_scope_torchaudio_quirk(fe):
+    import torchaudio.transforms as T
+    x = synth.s3_edge(8000)[4:6]
+    lf = T.LFCC(**LFCC_CFG)
+    coupled = lf(torch.from_numpy(x)).numpy()
+    per_utt = lf(torch.from_numpy(x).unsqueeze(1)).squeeze(1).numpy()
+    m = fe.LFCC(**LFCC_CFG, top_db_scope="torchaudio")
+    assert_feat_close(m(cuda(x)).cpu().numpy(), coupled, 2e-4, "2-D input, torchaudio scope")
+    assert_feat_close(m(cuda(x).unsqueeze(1)).squeeze(1).cpu().numpy(), per_utt, 2e-4, "3-D input")
+    assert_feat_close(fe.LFCC(**LFCC_CFG)(cuda(x)).cpu().numpy(), per_utt, 2e-4, "utterance scope")
+
+
+def test_edge_inputs_are_total(fe):
+    """All-zero utterances (the reference emits them for unreadable files, maze5.py:313-319) give
+    finite -100 dB features; impulses at both ends exercise the reflect padding."""
+    m = fe.LFCCDelta(**LFCC_CFG)
+    x = synth.s3_edge()
+    out = m(cuda(x)).cpu().numpy()
+    assert np.isfinite(out).all()
+    ref = LFCCDeltaRef()(torch.from_numpy(x)).numpy()
+    assert_feat_close(out, ref, TOL, "edge set S3")
+    z = out[0]
+    assert np.abs(z[0] - ref[0, 0]).max() < 1e-3 and np.abs(z[1:]).max() < 1e-3  # only c0 is non-zero
+
+
+def test_ragged_repeat_pad(fe):
+    """Config 5 input contract: clips of 1-10 s repeat-padded / truncated to 64600 in the loader."""
+    flat, offsets, lengths = synth.s4_ragged(24)
+    lengths[0], lengths[1] = 64600, 64601
+    dense = np.stack([O.pad_repeat(flat[o:o + l], 64600) for o, l in zip(offsets, lengths)])
+    m = fe.LFCCDelta(**LFCC_CFG)
+    a = m.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600)
+    b = m(cuda(dense))
+    assert a.shape == (24, 60, 404)
+    assert torch.equal(a, b)
+    ref = LFCCDeltaRef()(torch.from_numpy(dense)).numpy()
+    assert_feat_close(a.cpu().numpy(), ref, TOL, "ragged vs torchaudio on pad()-ed clips")
+
+
+def test_cmvn_extension(fe):
+    x = synth.s1_noise(3)
+    out = fe.LFCCDelta(**LFCC_CFG, cmvn=True)(cuda(x)).cpu().numpy()
+    ref = O.lfcc(x, deltas=2, do_cmvn=True)
+    assert np.abs(out - ref).max() < 2e-3
+    assert np.abs(out.mean(-1)).max() < 1e-4
+
+
+def test_host_buffer_path_equals_device_path(fe):
+    m = fe.LFCCDelta(**LFCC_CFG)
+    x = synth.s1_noise(300)
+    xh = torch.from_numpy(x).pin_memory()
+    out_h = m.forward_host(xh, chunk_rows=64, n_streams=3)
+    out_d = m(cuda(x)).cpu()
+    assert out_h.shape == (300, 60, 404)
+    assert torch.equal(out_h, out_d)
+
+
+def test_chunking_is_invisible(fe):
+    """More rows than one workspace chunk (and than one wave of CTAs): same bits as small batches."""
+    m = fe.LFCCDelta(**LFCC_CFG)
+    x = cuda(synth.s1_noise(8)).repeat(260, 1)  # 2080 rows > chunk of ~1500
+    out = m(x)
+    assert torch.equal(out[:8], out[2072:])
+    assert torch.equal(out[:8], m(x[:8]))
+
+
+def test_full_size_properties(fe):
+    """BASELINE config 2 size (4096 utterances): size-independent properties instead of a CPU
+    comparison — batch replication invariance and delta linearity/consistency."""
+    m = fe.LFCCDelta(**LFCC_CFG)
+    base = cuda(synth.s1_noise(16))
+    x = base.repeat(256, 1)
+    out = m(x)
+    assert out.shape == (4096, 60, 404)
+    assert torch.isfinite(out).all()
+    assert torch.equal(out.reshape(256, 16, 60, 404)[0], out.reshape(256, 16, 60, 404)[255])
+    # delta block equals ComputeDeltas of the static block; delta-delta likewise
+    d = fe.ComputeDeltas()(out[:64, :20].contiguous())
+    assert (d - out[:64, 20:40]).abs().max() < 1e-5
+    dd = fe.ComputeDeltas()(out[:64, 20:40].contiguous())
+    assert (dd - out[:64, 40:60]).abs().max() < 1e-5
+
+
+def test_c_abi_error_paths_on_device(fe):
+    lib = fe._lib.load()
+    m = fe.LFCCDelta(**LFCC_CFG)
+    eng = m.engine
+    x = cuda(synth.s1_noise(2))
+    out = torch.empty(2, 60, 404, device=dev())
+    tables = eng.tables_on(dev())
+    ws = torch.empty(1024, dtype=torch.uint8, device=dev())
+    rc = lib.b200fe_features_forward(x.data_ptr(), 2, 64600, None, None, C.byref(eng.params), tables.data_ptr(),
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == -3  # workspace too small
+    rc = lib.b200fe_features_forward(None, 2, 64600, None, None, C.byref(eng.params), tables.data_ptr(),
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == -1
+    rc = lib.b200fe_features_forward(x.data_ptr(), 2, 100, None, None, C.byref(eng.params), tables.data_ptr(),
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == -1  # T <= n_fft/2: reflect padding impossible (torch.stft raises too)
+
+
+def test_stream_and_graph_capture(fe):
+    """Work goes to the caller's stream and is CUDA-graph capturable."""
+    m = fe.LFCCDelta(**LFCC_CFG)
+    x = cuda(synth.s1_noise(8))
+    expect = m(x).clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out_s = m(x)
+    s.synchronize()
+    assert torch.equal(out_s, expect)
+    out_g = torch.empty_like(expect)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        m.engine.features(x, out=out_g)
+    out_g.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out_g, expect)
