@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(kFftThreads) fe_fft_kernel(fe_fft_args a) {
   off += (size_t)nh * 8;
   fe_c2* s_rtw = reinterpret_cast<fe_c2*>(smem_raw + off);
   off += (((size_t)(nh / 2 + 1) * 8) + 15) & ~(size_t)15;
-  fe_c2* s_buf = reinterpret_cast<fe_c2*>(smem_raw + off);  // [warps][2][nh+1]
-  off += (size_t)kFftWarps * 2 * (nh + 1) * 8;
+  fe_c2* s_buf = reinterpret_cast<fe_c2*>(smem_raw + off);  // [fft_warps][2][nh+1]
+  off += (size_t)a.fft_warps * 2 * (nh + 1) * 8;
   float* s_tile = reinterpret_cast<float*>(smem_raw + off);  // MODE0: [n_freq][ft+1]; MODE1: [n_filter][ft+1]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(kFftThreads) fe_fft_kernel(fe_fft_args a) {
   const int32_t* bwoff = reinterpret_cast<const int32_t*>(blob + h->off_band_woff);
   const float* bw = reinterpret_cast<const float*>(blob + h->off_band_w);
 
-  for (int fl = warp; fl < nf_here; fl += kFftWarps) {
+  // only the first fft_warps warps own FFT buffers (all 8 unless n_fft is too large for shared memory)
+  for (int fl = warp; fl < nf_here && warp < a.fft_warps; fl += a.fft_warps) {
     const float* frame = s_stage + (size_t)fl * hop;
     fe_c2* in = buf0;
     fe_c2* out = buf1;
@@ -250,17 +251,25 @@ cudaError_t set_smem(const void* fn, size_t bytes) {
 
 }  // namespace
 
+int fe_fft_warps_for(int n_fft) {
+  // per-warp ping-pong buffers: 2 * (n_fft/2 + 1) complex; keep them within ~96 KB
+  int w = (96 * 1024) / (2 * (n_fft / 2 + 1) * 8);
+  return w > kFftWarps ? kFftWarps : (w < 1 ? 1 : w);
+}
+
 size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch) {
   const int nh = n_fft / 2;
   size_t seg = (size_t)(ft - 1) * hop + n_fft;
   size_t b = (seg * 4 + 15) & ~(size_t)15;
   b += (size_t)n_fft * 4 + (size_t)nh * 8 + ((((size_t)(nh / 2 + 1)) * 8 + 15) & ~(size_t)15);
-  b += (size_t)kFftWarps * 2 * (nh + 1) * 8;
+  b += (size_t)fe_fft_warps_for(n_fft) * 2 * (nh + 1) * 8;
   b += (size_t)n_ch * (ft + 1) * 4;
   return b;
 }
 
-cudaError_t fe_launch_fft(const fe_fft_args& a, int mode, int64_t rows, cudaStream_t stream) {
+cudaError_t fe_launch_fft(const fe_fft_args& a_in, int mode, int64_t rows, cudaStream_t stream) {
+  fe_fft_args a = a_in;
+  a.fft_warps = fe_fft_warps_for(a.n_fft);
   const int n_ch = mode == 0 ? a.n_fft / 2 + 1 : a.n_filter;
   const size_t smem = fe_fft_smem_bytes(a.n_fft, a.hop, a.ft, n_ch);
   const int64_t grid = rows * a.tiles_per_row;

@@ -17,6 +17,7 @@ struct fe_fft_args {
   int32_t ft;               // frames per CTA
   int32_t tiles_per_row;
   int32_t radix2_first;     // log2(n_fft/2) odd
+  int32_t fft_warps;        // warps that own FFT buffers (set by fe_launch_fft)
   int32_t top_db_group;
   float preemph;
 };
