@@ -171,8 +171,20 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
     return B200FE_ERR_WORKSPACE;
   }
   if (((uintptr_t)workspace & 15) != 0) { fe_set_error("workspace must be 16-byte aligned"); return B200FE_ERR_ALIGNMENT; }
-  const int32_t variant = b200fe_resolve_variant(p);
-  if (variant < 0) return variant;
+  // AUTO is resolved by the caller against the host copy of the tables (b200fe_tables_variant);
+  // a forward call that still says AUTO only sees the device copy and takes the FFT variant.
+  int32_t variant = B200FE_VARIANT_FFT;
+  if (p->variant == B200FE_VARIANT_DFT_GEMM) {
+    if (!fe_gemm_supported(p) || offsets != nullptr) {
+      fe_set_error("variant dft_gemm does not support this configuration / ragged input");
+      return B200FE_ERR_UNSUPPORTED;
+    }
+    if ((T & 3) != 0 || ((uintptr_t)wave & 15) != 0) {
+      fe_set_error("variant dft_gemm needs T %% 4 == 0 and a 16-byte aligned waveform (TMA)");
+      return B200FE_ERR_UNSUPPORTED;
+    }
+    variant = B200FE_VARIANT_DFT_GEMM;
+  }
 
   cudaStream_t stream = (cudaStream_t)stream_;
   const int n_frames = (int)(1 + T / p->hop_length);

@@ -43,9 +43,9 @@ struct fe_blob_header {
   int32_t gemm_nhalf;      // n_fft/4 : GEMM N (bins 0 .. n_fft/4-1; bin n_fft/4 handled apart)
   int32_t off_gemm_b;      // __half operand tiles, see fe_gemm.cuh
   int32_t gemm_b_bytes;
-  int32_t off_gemm_fb;     // float4[gemm_nhalf + 1] sliding filterbank table, see fe_gemm.cuh
-  int32_t off_gemm_fbflag; // int32[gemm_nhalf + 1]
-  int32_t off_gemm_mid;    // float[2*gemm_kpairs*2]  weights for bin n_fft/4 (cos-even, sin-odd rows)
+  int32_t off_gemm_fb;     // fe_gemm_fb_entry[gemm_nhalf + 1] sliding filterbank table (fe_gemm_layout.h)
+  int32_t off_gemm_fbflag; // unused
+  int32_t off_gemm_mid;    // float[2][gemm_kpairs]  true-unit weights of bin n_fft/4 (Re from a_e, Im from a_o)
   int32_t reserved[8];
 };
 

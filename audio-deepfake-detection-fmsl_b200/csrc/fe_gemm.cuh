@@ -1,0 +1,153 @@
+// Per-thread arithmetic of the DFT-GEMM variant (see fe_gemm_layout.h for the math and layouts).
+// Everything here compiles for the device (used by fe_gemm.cu) and as plain C++ (tests/emu), so the
+// fold / scale / fp16-split / filterbank-sweep logic is exercised on the CPU with the MMA replaced by
+// loops over the very same operand images.
+#ifndef FE_GEMM_CUH_
+#define FE_GEMM_CUH_
+
+#include <math.h>
+#include <string.h>
+#include <cuda_fp16.h>
+
+#include "fe_gemm_layout.h"
+
+struct alignas(16) fe_u4 {
+  uint32_t x, y, z, w;
+};
+
+FE_HD uint32_t fe_f2u(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+FE_HD float fe_u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+// Two floats -> packed fp16 pair (first in the low half) with round-to-nearest, and the residuals
+// v - fp16(v) (exact in fp32) for the lo parts.
+FE_HD uint32_t fe_pack_hi(float a, float b, float& ra, float& rb) {
+#ifdef __CUDA_ARCH__
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 back = __half22float2(h);
+  ra = a - back.x;
+  rb = b - back.y;
+  return *reinterpret_cast<const uint32_t*>(&h);
+#else
+  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+  ra = a - __half2float(ha);
+  rb = b - __half2float(hb);
+  uint16_t ua, ub;
+  memcpy(&ua, &ha, 2);
+  memcpy(&ub, &hb, 2);
+  return (uint32_t)ua | ((uint32_t)ub << 16);
+#endif
+}
+FE_HD uint32_t fe_pack_lo(float a, float b) {
+  float ra, rb;
+  return fe_pack_hi(a, b, ra, rb);
+}
+
+// Per-frame power-of-two scale: `bound` >= max |a_e|, |a_o| of the frame (2 * max|x| over its two hop
+// blocks).  scale * bound lies in [2^13, 2^14), so the fp16 hi parts keep 11 significant bits and the lo
+// parts stay normal numbers; `unscale` = 1 / (scale * 2^14) undoes it (and the 2^14 of the DFT tiles)
+// on the amplitude, i.e. power_true = power_acc * unscale^2.
+FE_HD void fe_gemm_frame_scale(float bound, float& scale, float& unscale) {
+  const uint32_t eb = (fe_f2u(bound) >> 23) & 0xffu;
+  int e = (int)eb - 127;               // bound in [2^e, 2^(e+1))
+  if (eb == 0u || eb == 0xffu) e = FE_GEMM_A_SCALE_LOG2;   // zero / subnormal / non-finite: scale 1
+  int s = FE_GEMM_A_SCALE_LOG2 - e;
+  s = s > 100 ? 100 : (s < -100 ? -100 : s);
+  scale = fe_u2f((uint32_t)(s + 127) << 23);
+  unscale = fe_u2f((uint32_t)(-s - FE_GEMM_B_SCALE_LOG2 + 127) << 23);
+}
+
+// One half stage (16 sample pairs j = j0 .. j0+15, j0 a multiple of 16) of one frame:
+//   fwd[i] = x[c + j0 + i]        bwd[i] = x[c - j0 - i]          i = 0 .. 15
+// Produces the eight 16-byte K chunks (one per sub-GEMM x flavour) of the frame's A rows and updates
+// the directly evaluated bin n_fft/4 (true units).
+//   chunk[(sub*2 + flav)], sub: 0 = ce (a_e, even j), 1 = co (a_e, odd j), 2 = se (a_o, even j), 3 = so (a_o, odd j)
+FE_HD void fe_gemm_produce_half(const float* fwd, const float* bwd, float scale, int j0, const float* mid_re_w,
+                                const float* mid_im_w, float& mid_re, float& mid_im, fe_u4* chunk) {
+  uint32_t hi[4][4], lo[4][4];  // [sub][word]: 8 halfs = 4 words per chunk
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    // word w of the even-j chunk holds j = j0 + 4w, j0 + 4w + 2 ; of the odd-j chunk j0 + 4w + 1, + 3
+    const int i0 = 4 * w;
+    const float ae0 = fwd[i0] + bwd[i0], ao0 = fwd[i0] - bwd[i0];
+    const float ae1 = fwd[i0 + 1] + bwd[i0 + 1], ao1 = fwd[i0 + 1] - bwd[i0 + 1];
+    const float ae2 = fwd[i0 + 2] + bwd[i0 + 2], ao2 = fwd[i0 + 2] - bwd[i0 + 2];
+    const float ae3 = fwd[i0 + 3] + bwd[i0 + 3], ao3 = fwd[i0 + 3] - bwd[i0 + 3];
+    mid_re = fmaf(ae0, mid_re_w[j0 + i0], mid_re);
+    mid_re = fmaf(ae2, mid_re_w[j0 + i0 + 2], mid_re);
+    mid_im = fmaf(ao1, mid_im_w[j0 + i0 + 1], mid_im);
+    mid_im = fmaf(ao3, mid_im_w[j0 + i0 + 3], mid_im);
+    float r0, r1;
+    hi[0][w] = fe_pack_hi(ae0 * scale, ae2 * scale, r0, r1); lo[0][w] = fe_pack_lo(r0, r1);
+    hi[1][w] = fe_pack_hi(ae1 * scale, ae3 * scale, r0, r1); lo[1][w] = fe_pack_lo(r0, r1);
+    hi[2][w] = fe_pack_hi(ao0 * scale, ao2 * scale, r0, r1); lo[2][w] = fe_pack_lo(r0, r1);
+    hi[3][w] = fe_pack_hi(ao1 * scale, ao3 * scale, r0, r1); lo[3][w] = fe_pack_lo(r0, r1);
+  }
+#pragma unroll
+  for (int sub = 0; sub < 4; ++sub) {
+    chunk[sub * 2 + 0] = fe_u4{hi[sub][0], hi[sub][1], hi[sub][2], hi[sub][3]};
+    chunk[sub * 2 + 1] = fe_u4{lo[sub][0], lo[sub][1], lo[sub][2], lo[sub][3]};
+  }
+}
+
+// ---- epilogue: power of bins k and n_fft/2 - k from the four accumulators, swept through the
+// triangular filterbank with two sliding windows (ascending bins k, descending bins n_fft/2 - k) ----
+struct fe_gemm_epi_state {
+  float lo0, lo1, hi0, hi1;
+  int phi_lo, phi_hi;
+};
+
+FE_HD void fe_gemm_epi_init(fe_gemm_epi_state& st, const fe_gemm_fb_entry& first) {
+  st.lo0 = st.lo1 = st.hi0 = st.hi1 = 0.0f;
+  st.phi_lo = first.phi_lo;
+  st.phi_hi = first.phi_hi;
+}
+
+template <class Emit>
+FE_HD void fe_gemm_epi_bin(fe_gemm_epi_state& st, const fe_gemm_fb_entry& t, float ce, float co, float se, float so,
+                           Emit&& emit) {
+  const float re1 = ce + co, im1 = se + so, re2 = ce - co, im2 = so - se;
+  const float p1 = fmaf(re1, re1, im1 * im1);  // |X[k]|^2           (scaled units)
+  const float p2 = fmaf(re2, re2, im2 * im2);  // |X[n_fft/2 - k]|^2
+  while (st.phi_lo < t.phi_lo) {
+    emit(st.phi_lo, st.lo0);
+    st.lo0 = st.lo1;
+    st.lo1 = 0.0f;
+    ++st.phi_lo;
+  }
+  st.lo0 = fmaf(p1, t.w_lo_a, st.lo0);
+  st.lo1 = fmaf(p1, t.w_lo_b, st.lo1);
+  while (st.phi_hi > t.phi_hi) {
+    emit(st.phi_hi + 1, st.hi1);
+    st.hi1 = st.hi0;
+    st.hi0 = 0.0f;
+    --st.phi_hi;
+  }
+  st.hi0 = fmaf(p2, t.w_hi_a, st.hi0);
+  st.hi1 = fmaf(p2, t.w_hi_b, st.hi1);
+}
+
+template <class Emit>
+FE_HD void fe_gemm_epi_flush(fe_gemm_epi_state& st, Emit&& emit) {
+  emit(st.phi_lo, st.lo0);
+  emit(st.phi_lo + 1, st.lo1);
+  emit(st.phi_hi, st.hi0);
+  emit(st.phi_hi + 1, st.hi1);
+}
+
+#endif  // FE_GEMM_CUH_

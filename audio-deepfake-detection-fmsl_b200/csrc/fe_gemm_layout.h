@@ -1,0 +1,43 @@
+// Data layout shared by the host packer (fe_gemm_tables.cpp), the tcgen05 kernel (fe_gemm.cu) and
+// the CPU emulation (tests/emu) of the DFT-GEMM variant.
+//
+// Math.  A frame is win = 2*hop samples centred on c (torch.stft center=True); with the symmetric
+// window w(j) = w(-j) at offset j from the centre and the folded samples
+//     a_e[j] = x[c+j] + x[c-j],   a_o[j] = x[c+j] - x[c-j],   j = 0 .. win/2-1   (a_e[0] = 2 x[c])
+// the spectrum is  Re X[k] = sum_j a_e[j] h(j) w(j) cos(2 pi k j / n_fft),  h(0) = 1/2, h(j>0) = 1
+//                  Im X[k] = - sum_j a_o[j] w(j) sin(2 pi k j / n_fft)      (up to the sign (-1)^k).
+// Splitting j by parity gives four sums  ce, co (cos, even / odd j)  and  se, so (sin, even / odd j)
+// with  X[k] = (ce+co) + i(se+so)  and  X[n_fft/2 - k] = (ce-co) + i(so-se), so bins 0..n_fft/4-1
+// (columns of the GEMM) yield all bins except n_fft/4, which the producer evaluates directly.
+// Each of the four sums is a GEMM  [128 frames x 16*stages] x [16*stages x n_fft/4]  evaluated as three
+// fp16 products  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  accumulated in fp32 in TMEM.
+#ifndef FE_GEMM_LAYOUT_H_
+#define FE_GEMM_LAYOUT_H_
+
+#include "fe_common.h"
+
+#define FE_GEMM_MAX_FILTERS 32
+#define FE_GEMM_TILE_M 128        // frames per tile = TMEM lanes
+#define FE_GEMM_B_SCALE_LOG2 14   // DFT matrix entries are stored times 2^14 (lo parts stay normal fp16)
+#define FE_GEMM_A_SCALE_LOG2 13   // per frame: 2*max|x| is scaled into [2^13, 2^14)
+#define FE_GEMM_STAGE_J 32        // sample pairs per pipeline stage: one K=16 MMA step per sub-GEMM
+
+// sliding triangular-filterbank table, one entry per GEMM column k (bins k and n_fft/2 - k)
+struct alignas(16) fe_gemm_fb_entry {
+  float w_lo_a, w_lo_b;   // weights of bin k for filters phi_lo, phi_lo + 1
+  float w_hi_a, w_hi_b;   // weights of bin n_fft/2 - k for filters phi_hi, phi_hi + 1
+  int32_t phi_lo, phi_hi;
+  int32_t pad0, pad1;
+};
+
+// UMMA K-major, no-swizzle operand tile of `rows` rows x 16 K-values (one K=16 MMA step):
+// [K chunk of 8][row][8 halfs] -> descriptor LBO (K-chunk stride) = rows*16 B, SBO (8-row group) = 128 B.
+FE_HD int fe_gemm_operand_offset(int rows, int r, int kk) { return (kk >> 3) * rows * 16 + r * 16 + (kk & 7) * 2; }
+FE_HD int fe_gemm_tile_bytes(int rows) { return 2 * rows * 16; }
+// a stage holds [sub-GEMM 4: ce co se so][flavour 2: hi lo] tiles
+FE_HD int fe_gemm_b_tile_offset(int nhalf, int sub, int flav) { return (sub * 2 + flav) * fe_gemm_tile_bytes(nhalf); }
+FE_HD int fe_gemm_b_stage_bytes(int nhalf) { return 8 * fe_gemm_tile_bytes(nhalf); }
+FE_HD int fe_gemm_a_tile_offset(int sub, int flav) { return (sub * 2 + flav) * fe_gemm_tile_bytes(FE_GEMM_TILE_M); }
+FE_HD int fe_gemm_a_stage_bytes() { return 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M); }
+
+#endif  // FE_GEMM_LAYOUT_H_

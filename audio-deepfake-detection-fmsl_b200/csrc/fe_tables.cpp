@@ -227,3 +227,22 @@ extern "C" int32_t b200fe_tables_pack(const b200fe_params* p, const float* windo
   (void)n_freq;
   return B200FE_OK;
 }
+
+extern "C" int32_t b200fe_tables_variant(const b200fe_params* p, const void* blob_host) {
+  int32_t st = fe_validate_params(p);
+  if (st != B200FE_OK) return st;
+  if (!blob_host) { fe_set_error("blob_host is NULL"); return B200FE_ERR_BAD_ARG; }
+  const fe_blob_header* h = (const fe_blob_header*)blob_host;
+  if (h->magic != FE_BLOB_MAGIC) { fe_set_error("blob_host is not a packed tables blob"); return B200FE_ERR_BAD_ARG; }
+  const bool gemm_ok = h->gemm_ok != 0 && fe_gemm_variant_built();
+  if (p->variant == B200FE_VARIANT_FFT) return B200FE_VARIANT_FFT;
+  if (p->variant == B200FE_VARIANT_DFT_GEMM) {
+    if (!gemm_ok) {
+      fe_set_error("variant dft_gemm is not available for this configuration (needs win_length == 2*hop_length, "
+                   "n_fft <= 512, symmetric window with window[0] == 0, triangular filterbank, n_filter <= 32)");
+      return B200FE_ERR_UNSUPPORTED;
+    }
+    return B200FE_VARIANT_DFT_GEMM;
+  }
+  return (gemm_ok && fe_gemm_auto_prefers(p)) ? B200FE_VARIANT_DFT_GEMM : B200FE_VARIANT_FFT;
+}

@@ -154,6 +154,10 @@ class FrontEndEngine:
         d_a, d_p = _as_f32_ptr(dct)
         _lib.check(self.lib.b200fe_tables_pack(C.byref(p), w_p, f_p, d_p,
                                                self._blob_host.ctypes.data_as(C.c_void_p), nbytes))
+        # resolve 'auto' (and validate an explicit request) against what these tables support
+        resolved = _lib.check(self.lib.b200fe_tables_variant(C.byref(p), self._blob_host.ctypes.data_as(C.c_void_p)))
+        self.requested_variant = variant
+        p.variant = resolved
         self._blob_dev: Dict[torch.device, Tensor] = {}
         self._workspace: Dict[torch.device, Tensor] = {}
 
@@ -166,8 +170,7 @@ class FrontEndEngine:
         return _lib.check(self.lib.b200fe_n_out_channels(C.byref(self.params)))
 
     def resolved_variant(self) -> str:
-        v = _lib.check(self.lib.b200fe_resolve_variant(C.byref(self.params)))
-        return {1: "fft", 2: "dft_gemm"}[v]
+        return {1: "fft", 2: "dft_gemm"}[int(self.params.variant)]
 
     def last_launch_count(self) -> int:
         return int(self.lib.b200fe_last_launch_count())

@@ -104,6 +104,15 @@ int64_t b200fe_tables_bytes(const b200fe_params* p);
 int32_t b200fe_tables_pack(const b200fe_params* p, const float* window, const float* fbank,
                            const float* dct, void* blob_host, size_t blob_bytes);
 
+/* Which kernel family the forward calls should use with THIS packed blob: resolves
+ * B200FE_VARIANT_AUTO (and validates an explicit request) against what the tables support — the
+ * DFT-GEMM variant needs win_length == 2*hop_length, n_fft in {128..512}, a window symmetric about
+ * the frame centre with window[0] == 0 (periodic Hann) and a triangular filterbank whose bins feed
+ * at most two adjacent filters.  Returns B200FE_VARIANT_FFT / _DFT_GEMM, or an error when an
+ * explicitly requested variant is not available.  Callers store the answer in params.variant;
+ * forward calls given B200FE_VARIANT_AUTO use the FFT variant (they only see the device copy). */
+int32_t b200fe_tables_variant(const b200fe_params* p, const void* blob_host);
+
 /* ---- device entry points -------------------------------------------------------------------- */
 /* Scratch needed by b200fe_features_forward for R rows of T samples (filterbank energies of one
  * chunk of rows + per-group maxima).  <0 on bad args. */

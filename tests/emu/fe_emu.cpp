@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 #include "fe_fft.cuh"
@@ -111,6 +112,125 @@ extern "C" int fe_emu_features(const float* wave, int64_t R, int64_t T, const in
       float* out_row = out + (size_t)row * n_out * nF;
       for (int tid = 0; tid < tthreads; ++tid)
         fe_tail_store(tid, tthreads, s_c, s_d.data(), nc, w, n, halo, t0, nt_here, nF, p->deltas, out_row);
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CPU emulation of the DFT-GEMM variant (fe_gemm.cu): the same per-thread functions (fe_gemm.cuh) and the
+// same operand images / tables (fe_gemm_layout.h), with tcgen05.mma replaced by loops that decode the
+// fp16 operand tiles at their UMMA layout offsets and accumulate in fp32.  Output: filterbank energies
+// [R][n_filter][nF] (what fe_gemm_kernel writes to the workspace).
+// ---------------------------------------------------------------------------------------------------
+#include "fe_gemm.cuh"
+
+static float emu_half_at(const unsigned char* img, int off) {
+  __half h;
+  memcpy(&h, img + off, 2);
+  return __half2float(h);
+}
+
+static int emu_reflect(int s, int T) {
+  if (s < 0) s = -s;
+  if (s >= T) s = 2 * (T - 1) - s;
+  return s;
+}
+
+static float emu_absmax(const float* x, int lo, int hi) {
+  float m = 0.0f;
+  for (int i = lo; i < hi; ++i) m = fmaxf(m, fabsf(x[i]));
+  return m;
+}
+
+extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, const b200fe_params* p,
+                                    const void* tables, float* energies) {
+  const unsigned char* blob = (const unsigned char*)tables;
+  const fe_blob_header* h = (const fe_blob_header*)blob;
+  if (h->magic != FE_BLOB_MAGIC || !h->gemm_ok) return -1;
+  const int T = (int)T_, hop = p->hop_length, nF = 1 + T / hop, nfil = p->n_filter;
+  const int kpairs = h->gemm_kpairs, nhalf = h->gemm_nhalf, nstages = kpairs / 32;
+  const int nb_full = T / hop;
+  const fe_gemm_fb_entry* fb = (const fe_gemm_fb_entry*)(blob + h->off_gemm_fb);
+  const float* mid = (const float*)(blob + h->off_gemm_mid);
+  const unsigned char* gB = blob + h->off_gemm_b;
+  const int M = FE_GEMM_TILE_M;
+  std::vector<unsigned char> a_stage(fe_gemm_a_stage_bytes());
+  std::vector<float> D((size_t)4 * M * nhalf), E((size_t)FE_GEMM_MAX_FILTERS * M);
+  const int tiles = (nF + M - 1) / M;
+  for (int64_t row = 0; row < R; ++row) {
+    const float* x = wave + row * T_;
+    for (int tile = 0; tile < tiles; ++tile) {
+      const int t0 = tile * M;
+      std::fill(D.begin(), D.end(), 0.0f);
+      std::fill(E.begin(), E.end(), 0.0f);
+      std::vector<float> scale(M), unscale(M), mre(M, 0.0f), mim(M, 0.0f);
+      // scout + frame scale
+      std::vector<float> bm(M + 1);
+      for (int s = 0; s <= M; ++s) {
+        const int b = t0 - 1 + s;
+        if (b < 0) bm[s] = emu_absmax(x, 0, std::min(T, 2 * hop + 1));
+        else if (b >= nb_full) bm[s] = emu_absmax(x, std::max(0, (nb_full - 2) * hop), T);
+        else bm[s] = emu_absmax(x, b * hop, (b + 1) * hop);
+      }
+      for (int m = 0; m < M; ++m) fe_gemm_frame_scale(2.0f * fmaxf(bm[m], bm[m + 1]), scale[m], unscale[m]);
+      for (int q = 0; q < nstages; ++q) {
+        // producers
+        for (int m = 0; m < M; ++m) {
+          const int t = t0 + m, c = t * hop;
+          const bool valid = t < nF;
+          for (int half = 0; half < 2; ++half) {
+            const int j0 = 32 * q + 16 * half;
+            float fwd[16], bwd[16];
+            for (int i = 0; i < 16; ++i) {
+              fwd[i] = valid ? x[emu_reflect(c + j0 + i, T)] : 0.0f;
+              bwd[i] = valid ? x[emu_reflect(c - j0 - i, T)] : 0.0f;
+            }
+            fe_u4 chunk[8];
+            fe_gemm_produce_half(fwd, bwd, scale[m], j0, mid, mid + kpairs, mre[m], mim[m], chunk);
+            for (int sf = 0; sf < 8; ++sf)
+              memcpy(a_stage.data() + sf * fe_gemm_tile_bytes(M) + fe_gemm_operand_offset(M, m, 8 * half), &chunk[sf], 16);
+          }
+        }
+        // "tcgen05.mma": D_sub += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo over the stage's 16 K values
+        const unsigned char* b_stage = gB + (size_t)q * fe_gemm_b_stage_bytes(nhalf);
+        for (int sub = 0; sub < 4; ++sub)
+          for (int m = 0; m < M; ++m)
+            for (int n = 0; n < nhalf; ++n) {
+              float acc = D[((size_t)sub * M + m) * nhalf + n];
+              for (int kk = 0; kk < 16; ++kk) {
+                const float ah = emu_half_at(a_stage.data(), fe_gemm_a_tile_offset(sub, 0) + fe_gemm_operand_offset(M, m, kk));
+                const float al = emu_half_at(a_stage.data(), fe_gemm_a_tile_offset(sub, 1) + fe_gemm_operand_offset(M, m, kk));
+                const float bh = emu_half_at(b_stage, fe_gemm_b_tile_offset(nhalf, sub, 0) + fe_gemm_operand_offset(nhalf, n, kk));
+                const float bl = emu_half_at(b_stage, fe_gemm_b_tile_offset(nhalf, sub, 1) + fe_gemm_operand_offset(nhalf, n, kk));
+                acc += ah * bh + al * bh + ah * bl;
+              }
+              D[((size_t)sub * M + m) * nhalf + n] = acc;
+            }
+      }
+      // epilogue: two column groups per frame
+      for (int m = 0; m < M; ++m) {
+        const float us = unscale[m];
+        auto emit = [&](int f, float v) {
+          if (f >= 0 && f < nfil && v != 0.0f) E[(size_t)f * M + m] += v * us * us;
+        };
+        for (int grp = 0; grp < 2; ++grp) {
+          const int kper = nhalf / 2, k_begin = grp * kper, k_end = k_begin + kper;
+          fe_gemm_epi_state st;
+          fe_gemm_epi_init(st, fb[k_begin]);
+          for (int k = k_begin; k < k_end; ++k)
+            fe_gemm_epi_bin(st, fb[k], D[((size_t)0 * M + m) * nhalf + k], D[((size_t)1 * M + m) * nhalf + k],
+                            D[((size_t)2 * M + m) * nhalf + k], D[((size_t)3 * M + m) * nhalf + k], emit);
+          fe_gemm_epi_flush(st, emit);
+        }
+        const fe_gemm_fb_entry tm = fb[nhalf];
+        const float pmid = mre[m] * mre[m] + mim[m] * mim[m];
+        if (tm.phi_lo >= 0 && tm.phi_lo < nfil) E[(size_t)tm.phi_lo * M + m] += pmid * tm.w_lo_a;
+        if (tm.phi_lo + 1 >= 0 && tm.phi_lo + 1 < nfil) E[(size_t)(tm.phi_lo + 1) * M + m] += pmid * tm.w_lo_b;
+      }
+      const int valid_rows = std::min(M, nF - t0);
+      for (int f = 0; f < nfil; ++f)
+        for (int r = 0; r < valid_rows; ++r) energies[((size_t)row * nfil + f) * nF + t0 + r] = E[(size_t)f * M + r];
     }
   }
   return 0;

@@ -91,7 +91,7 @@ def emulator():
         deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".h", ".cuh"))]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"),
-                                   "-I" + csrc, src, "-o", so])
+                                   "-I" + csrc, "-I/usr/local/cuda/include", src, "-o", so])
         _emu = C.CDLL(so)
     return _emu
 
@@ -114,3 +114,15 @@ def emulate(module, x, ft=32, tt=104, offsets=None, lengths=None, T=None, group=
         pw.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return out, pw
+
+
+def emulate_gemm_energies(module, x):
+    """CPU emulation of fe_gemm_kernel: filterbank energies (R, n_filter, n_frames)."""
+    eng = module.engine
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    R, T = x.shape
+    out = np.zeros((R, eng.params.n_filter, eng.n_frames(T)), np.float32)
+    rc = emulator().fe_emu_gemm_energies(x.ctypes.data_as(C.c_void_p), C.c_int64(R), C.c_int64(T), C.byref(eng.params),
+                                         eng._blob_host.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, "tables do not carry the DFT-GEMM variant"
+    return out
