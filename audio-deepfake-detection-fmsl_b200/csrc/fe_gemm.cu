@@ -24,14 +24,18 @@
 namespace {
 
 constexpr int kThreads = 512;
-constexpr int kProducerWarp0 = 4;
-constexpr int kEpilogueWarp0 = 8;
+constexpr int kScoutWarp0 = 2;      // warps 2, 3
+constexpr int kProducerWarp0 = 4;   // warps 4..7
+constexpr int kEpilogueWarp0 = 8;   // warps 8..15
 constexpr int kNumEpilogueWarps = 8;
 constexpr int kTileM = FE_GEMM_TILE_M;
-constexpr int kSampBoxBytes = kTileM * 128;       // 128 rows x 32 floats
+constexpr int kSampBoxBytes = kTileM * 128;         // 128 rows x 32 floats
 constexpr int kSampStageBytes = 2 * kSampBoxBytes;  // forward + backward box
 constexpr int kAStageBytes = 8 * 2 * kTileM * 16;   // 32 KB
-constexpr uint32_t kSpinLimit = 1u << 28;
+constexpr int kCellFloats = 128;                    // scout granularity: one coalesced 512-byte warp load
+constexpr int kMaxCells = 176;
+constexpr int kSideSlots = 3;                       // edge frames per tile: t = 0 and up to two at the end (slots in use: 1 + n_frames - nb_map)
+constexpr uint32_t kSpinLimit = 1u << 24;
 
 struct gemm_args {
   const float* wave;
@@ -42,34 +46,44 @@ struct gemm_args {
   int64_t T;
   int64_t row_base;
   int32_t rows, n_frames, n_filter, hop, nhalf, nstages, kpairs;
-  int32_t tiles_per_row, n_tiles, top_db_group, nb_full;
+  int32_t tiles_per_row, n_tiles, top_db_group, nb_map;
 };
 
 // ---- shared memory carve-up (offsets from a 1024-byte aligned base) -------------------------------
 struct smem_layout {
-  int samp, a_stage, b_stage, energies, fb, mid, bmax, unscale, p128, bars, total;
+  int samp, a_stage, b_stage, energies, fb, mid, cells, side, side_max, unscale, p128, bars, tmem_slot, total;
 };
 
-__host__ __device__ inline smem_layout make_layout(int nhalf, int kpairs) {
+__host__ __device__ inline smem_layout make_layout(int nhalf, int kpairs, int n_filter, int side_slots) {
   smem_layout L;
   int off = 0;
   L.samp = off;      off += 2 * kSampStageBytes;                        // 64 KB, 1024-aligned boxes
   L.a_stage = off;   off += 2 * kAStageBytes;                           // 64 KB
   L.b_stage = off;   off += 2 * fe_gemm_b_stage_bytes(nhalf);           // 64 KB at nhalf = 128
-  L.energies = off;  off += FE_GEMM_MAX_FILTERS * kTileM * 4;           // 16 KB
+  L.energies = off;  off += 2 * n_filter * kTileM * 4;                  // two column groups: 20 KB at 20 filters
   L.fb = off;        off += (nhalf + 1) * (int)sizeof(fe_gemm_fb_entry);
   L.mid = off;       off += 2 * kpairs * 4;
-  L.bmax = off;      off += 2 * 136 * 4;
+  L.cells = off;     off += 2 * kMaxCells * 4;
+  L.side = off;      off += 2 * side_slots * 2 * kpairs * 4;            // 5 KB at 160 pairs, 2 slots
+  L.side_max = off;  off += 2 * 4 * 4;
   L.unscale = off;   off += 2 * kTileM * 4;
   L.p128 = off;      off += 2 * kTileM * 4;
   off = (off + 15) & ~15;
   L.bars = off;      off += 16 * 8;
+  L.tmem_slot = off; off += 16;
   L.total = off;
   return L;
 }
 
 enum { BAR_SAMP_FULL = 0, BAR_STAGE_EMPTY = 2, BAR_A_FULL = 4, BAR_ACC_FULL = 6, BAR_ACC_EMPTY = 7,
        BAR_SCOUT_FULL = 8, BAR_SCOUT_EMPTY = 10, BAR_COUNT = 12 };
+
+#ifdef FE_GEMM_TRACE
+// debug build only: SM-clock timestamps of pipeline events of CTA 0 into the (enlarged) error-flag buffer
+#define FE_TRACE(ev, it, q) do { if (blockIdx.x == 0 && (it) < 8) { ((long long*)(a.error_flag + 64))[((it) * 8 + (q)) * 16 + (ev)] = clock64(); } } while (0)
+#else
+#define FE_TRACE(ev, it, q) do { } while (0)
+#endif
 
 // ---- PTX helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,21 +99,32 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the warp sleep in hardware instead of burning issue slots
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(2000u)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug turns into a reported error + trap instead of a hung GPU.
+__device__ __noinline__ void mbar_timeout(int* error_flag, int code) {
+#ifdef FE_GEMM_TRACE
+  // debug build: record who timed out first (code * 1000 + warp) and leave, so the flag can be read back
+  atomicCAS(error_flag, 0, code * 1000 + (int)(threadIdx.x >> 5));
+  __threadfence_system();
+  asm volatile("exit;");
+#else
+  atomicExch(error_flag, code);
+  __threadfence_system();
+  asm volatile("trap;");
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
   for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
     if (mbar_try_wait(bar, parity)) return;
   }
-  atomicExch(error_flag, code);
-  __threadfence_system();
-  asm volatile("trap;");
+  mbar_timeout(error_flag, code);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -161,22 +186,24 @@ __device__ __forceinline__ int reflect_idx(int s, int T) {
   return s;
 }
 
-// max |x| over [lo, hi) of one utterance, by a full warp (coalesced)
-__device__ __forceinline__ float warp_absmax(const float* x, int lo, int hi, int lane) {
-  float m = 0.0f;
-  for (int i = lo + lane; i < hi; i += 32) m = fmaxf(m, fabsf(__ldg(x + i)));
-  return warp_max(m);
+// edge-frame slot of frame t within its tile: 0 for t == 0, 1.. for frames whose forward block is not
+// covered by the tensor map (t >= nb_map); -1 for ordinary frames
+__device__ __forceinline__ int edge_slot(int t, int nb_map, int n_frames) {
+  if (t == 0) return 0;
+  if (t >= nb_map && t < n_frames) return 1 + (t - nb_map);
+  return -1;
 }
 
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
 fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  // dynamic shared memory is only guaranteed 16-byte aligned: round up to 1024 for the swizzled boxes
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint32_t tmem_base_s;
+  // round the dynamic window up to 1024 bytes (swizzled TMA boxes) without leaving the shared address space
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
-  const smem_layout L = make_layout(a.nhalf, a.kpairs);
+  const smem_layout L = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map);
+  const int side_slots = 1 + a.n_frames - a.nb_map;
+  const int side_floats = 2 * a.kpairs;  // per edge slot: forward[kpairs] + backward in box order [kpairs]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
@@ -184,9 +211,12 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
   float* s_energy = reinterpret_cast<float*>(smem + L.energies);
   fe_gemm_fb_entry* s_fb = reinterpret_cast<fe_gemm_fb_entry*>(smem + L.fb);
   float* s_mid = reinterpret_cast<float*>(smem + L.mid);
-  float* s_bmax = reinterpret_cast<float*>(smem + L.bmax);
+  float* s_cells = reinterpret_cast<float*>(smem + L.cells);
+  float* s_side = reinterpret_cast<float*>(smem + L.side);
+  float* s_side_max = reinterpret_cast<float*>(smem + L.side_max);
   float* s_unscale = reinterpret_cast<float*>(smem + L.unscale);
   float* s_p128 = reinterpret_cast<float*>(smem + L.p128);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const uint32_t bars = smem_u32(smem + L.bars);
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
 
@@ -196,7 +226,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
     for (int i = tid; i <= a.nhalf; i += kThreads) s_fb[i] = gfb[i];
     const float* gmid = reinterpret_cast<const float*>(blob + h->off_gemm_mid);
     for (int i = tid; i < 2 * a.kpairs; i += kThreads) s_mid[i] = gmid[i];
-    for (int i = tid; i < FE_GEMM_MAX_FILTERS * kTileM; i += kThreads) s_energy[i] = 0.0f;
+    for (int i = tid; i < 2 * a.n_filter * kTileM; i += kThreads) s_energy[i] = 0.0f;
   }
   if (tid == 0) {
     mbar_init(bar(BAR_SAMP_FULL + 0), 1);
@@ -207,20 +237,20 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
     mbar_init(bar(BAR_A_FULL + 1), 4);
     mbar_init(bar(BAR_ACC_FULL), 1);
     mbar_init(bar(BAR_ACC_EMPTY), kNumEpilogueWarps);
-    mbar_init(bar(BAR_SCOUT_FULL + 0), 1);
-    mbar_init(bar(BAR_SCOUT_FULL + 1), 1);
+    mbar_init(bar(BAR_SCOUT_FULL + 0), 2);
+    mbar_init(bar(BAR_SCOUT_FULL + 1), 2);
     mbar_init(bar(BAR_SCOUT_EMPTY + 0), 4);
     mbar_init(bar(BAR_SCOUT_EMPTY + 1), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = *s_tmem;
   const int T = (int)a.T;
   const int hop = a.hop;
 
@@ -230,17 +260,19 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
       asm volatile("prefetch.tensormap [%0];" ::"l"(&wave_map) : "memory");
       const uint32_t b_stage_bytes = (uint32_t)fe_gemm_b_stage_bytes(a.nhalf);
       const unsigned char* gB = blob + h->off_gemm_b;
-      uint32_t n = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      uint32_t n = 0, lit = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++lit) {
         const int row_local = tile / a.tiles_per_row;
         const int t0 = (tile - row_local * a.tiles_per_row) * kTileM;
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
           mbar_wait(bar(BAR_STAGE_EMPTY + s), par ^ 1u, a.error_flag, 1);
+          FE_TRACE(0, lit, q);
           mbar_arrive_expect_tx(bar(BAR_SAMP_FULL + s), 2u * kSampBoxBytes + b_stage_bytes);
           const uint32_t dst = smem_u32(smem + L.samp + s * kSampStageBytes);
-          // forward box: block t0 + m, columns 32q .. 32q+31 ; backward box: block t0 - 1 + m, columns
-          // hop - 32q - 32 .. hop - 32q - 1  (x[c - j], j = 32q+1 .. 32q+32, stored ascending in memory)
+          // forward box : block t0 + m,     columns 32q .. 32q+31        = x[c + 32q + e]
+          // backward box: block t0 - 1 + m, columns hop-32q-32 .. hop-32q-1 = x[c - 32q - 32 + e]
+          //               (16-byte aligned columns: an odd start column made the TMA fault)
           tma_box_3d(dst, &wave_map, bar(BAR_SAMP_FULL + s), 32 * q, t0, row_local);
           tma_box_3d(dst + kSampBoxBytes, &wave_map, bar(BAR_SAMP_FULL + s), hop - 32 * q - 32, t0 - 1, row_local);
           bulk_g2s(smem_u32(smem + L.b_stage + s * b_stage_bytes), gB + (size_t)q * b_stage_bytes, b_stage_bytes,
@@ -259,14 +291,16 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
         // accumulators of the previous tile must have been drained by the epilogue
         mbar_wait(bar(BAR_ACC_EMPTY), (it & 1u) ^ 1u, a.error_flag, 2);
         tc_fence_after();
+        FE_TRACE(7, it, 0);
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
           mbar_wait(bar(BAR_SAMP_FULL + s), par, a.error_flag, 3);   // DFT operand stage landed
           mbar_wait(bar(BAR_A_FULL + s), par, a.error_flag, 4);      // producers wrote the A stage
           tc_fence_after();
+          FE_TRACE(3, it, q);
           const uint32_t a_base = smem_u32(smem + L.a_stage + s * kAStageBytes);
           const uint32_t b_base = smem_u32(smem + L.b_stage + s * b_stage_bytes);
-#pragma unroll
+#pragma unroll 1
           for (int sub = 0; sub < 4; ++sub) {
             const uint64_t a_hi = make_desc(a_base + fe_gemm_a_tile_offset(sub, 0), kTileM * 16, 128);
             const uint64_t a_lo = make_desc(a_base + fe_gemm_a_tile_offset(sub, 1), kTileM * 16, 128);
@@ -282,10 +316,12 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
         }
       }
     }
-  } else if (warp == 2) {
-    // ================================ scout ===========================================================
-    // slot s of the tile <-> hop block t0 - 1 + s, s = 0 .. 128; frame m uses slots m (backward half) and
-    // m + 1 (forward half).  Blocks outside [0, nb_full) are bounded by the samples they reflect onto.
+  } else if (warp < kProducerWarp0) {
+    // ================================ scouts (warps 2, 3) =============================================
+    // Per-tile max|x| over 128-float cells (one coalesced warp load each) for the per-frame fp16 scale,
+    // one tile ahead of the producers; the reads also pull the tile's samples into L2 ahead of the TMA.
+    // Warp 2 additionally gathers the reflect-padded samples of edge frames into side buffers.
+    const int sw = warp - kScoutWarp0;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t pb = it & 1u;
@@ -293,111 +329,134 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
       const int row_local = tile / a.tiles_per_row;
       const int t0 = (tile - row_local * a.tiles_per_row) * kTileM;
       const float* x = a.wave + (a.row_base + row_local) * a.T;
-      float* bm = s_bmax + pb * 136;
-      for (int s = 0; s <= kTileM; ++s) {
-        const int b = t0 - 1 + s;
-        float m;
-        if (b < 0) m = warp_absmax(x, 0, min(T, 2 * hop + 1), lane);
-        else if (b >= a.nb_full) m = warp_absmax(x, max(0, (a.nb_full - 2) * hop), T, lane);
-        else m = warp_absmax(x, b * hop, (b + 1) * hop, lane);
-        if (lane == 0) bm[s] = m;
+      float* cells = s_cells + pb * kMaxCells;
+      const int c_first = max(0, (t0 - 1) * hop) / kCellFloats;
+      const int c_last = (min(T, (t0 + kTileM) * hop) - 1) / kCellFloats;
+      for (int c0 = c_first + sw; c0 <= c_last; c0 += 2 * 16) {
+        float4 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int c = c0 + 2 * u;
+          const int idx = c * kCellFloats + 4 * lane;
+          v[u] = (c <= c_last && idx < T) ? __ldg(reinterpret_cast<const float4*>(x + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int c = c0 + 2 * u;
+          const float mx = warp_max(fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+          if (lane == 0 && c <= c_last) cells[c - c_first] = mx;
+        }
+      }
+      if (sw == 0) {
+        for (int m = 0; m < kTileM; ++m) {
+          const int t = t0 + m;
+          const int slot = edge_slot(t, a.nb_map, a.n_frames);
+          if (slot < 0) {
+            if (t >= 1 && t < a.nb_map) { m = min(kTileM, a.nb_map - t0) - 1; }  // skip the ordinary frames
+            continue;
+          }
+          float* sf = s_side + (pb * side_slots + slot) * side_floats;
+          float* sb = sf + a.kpairs;
+          const int c = t * hop;
+          float mx = 0.0f;
+          for (int j = lane; j < a.kpairs; j += 32) {
+            const float f = __ldg(x + reflect_idx(c + j, T));
+            const int q = j >> 5, e = j & 31;
+            const float b = __ldg(x + reflect_idx(c - 32 * q - 32 + e, T));
+            sf[j] = f;
+            sb[j] = b;
+            mx = fmaxf(mx, fmaxf(fabsf(f), fabsf(b)));
+          }
+          mx = warp_max(mx);
+          if (lane == 0) s_side_max[pb * 4 + slot] = mx;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL + pb));
     }
-  } else if (warp >= kProducerWarp0 && warp < kProducerWarp0 + 4) {
-    // ================================ producers =======================================================
+  } else if (warp < kEpilogueWarp0) {
+    // ================================ producers (warps 4..7) ==========================================
     const int m = (warp - kProducerWarp0) * 32 + lane;  // tile row = TMEM lane
     const float* mid_re_w = s_mid;
     const float* mid_im_w = s_mid + a.kpairs;
+    const int swz = m & 7;
     uint32_t n = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t pb = it & 1u;
       const int row_local = tile / a.tiles_per_row;
       const int t0 = (tile - row_local * a.tiles_per_row) * kTileM;
       const int t = t0 + m;
-      const float* x = a.wave + (a.row_base + row_local) * a.T;
-      const int c = t * hop;
-      // frames whose two hop blocks are not both inside the tensor map read global memory directly
-      const bool edge = (t == 0) || (t >= a.nb_full);
-      const bool valid = t < a.n_frames;
+      const int slot = edge_slot(t, a.nb_map, a.n_frames);
       mbar_wait(bar(BAR_SCOUT_FULL + pb), (it >> 1) & 1u, a.error_flag, 6);
+      float bound = 0.0f;
+      if (slot >= 0) {
+        bound = s_side_max[pb * 4 + slot];
+      } else if (t < a.n_frames) {
+        const int c_first = max(0, (t0 - 1) * hop) / kCellFloats;
+        const int ca = ((t - 1) * hop) / kCellFloats - c_first, cb = ((t + 1) * hop - 1) / kCellFloats - c_first;
+        for (int cidx = ca; cidx <= cb; ++cidx) bound = fmaxf(bound, s_cells[pb * kMaxCells + cidx]);
+      }
       float scale, unscale;
-      fe_gemm_frame_scale(2.0f * fmaxf(s_bmax[pb * 136 + m], s_bmax[pb * 136 + m + 1]), scale, unscale);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_SCOUT_EMPTY + pb));
-      float mid_re = 0.0f, mid_im = 0.0f;
-      float carry = 0.0f;  // x[c - 32q], the backward sample the previous stage's box ended with
+      fe_gemm_frame_scale(2.0f * bound, scale, unscale);
+      // edge frames read their (reflect-padded) samples from the side buffer, laid out like one box row
+      const unsigned char* side_f = reinterpret_cast<const unsigned char*>(s_side + (pb * side_slots + (slot < 0 ? 0 : slot)) * side_floats);
+      const int my_swz = slot < 0 ? swz : 0;
+      float mid_re = 0.0f, mid_im = 0.0f, carry = 0.0f;
+#pragma unroll 1
       for (int q = 0; q < a.nstages; ++q, ++n) {
         const uint32_t s = n & 1u, par = (n >> 1) & 1u;
         mbar_wait(bar(BAR_SAMP_FULL + s), par, a.error_flag, 7);
-        const unsigned char* fbox = smem + L.samp + s * kSampStageBytes + m * 128;
-        const unsigned char* bbox = fbox + kSampBoxBytes;
-        unsigned char* a_stage = smem + L.a_stage + s * kAStageBytes;
-#pragma unroll
+        if (warp == kProducerWarp0 && lane == 0) FE_TRACE(1, it, q);
+        const unsigned char* fbox = slot < 0 ? smem + L.samp + s * kSampStageBytes + m * 128 : side_f + q * 128;
+        const unsigned char* bbox = slot < 0 ? fbox + kSampBoxBytes : side_f + a.kpairs * 4 + q * 128;
+        unsigned char* a_row = smem + L.a_stage + s * kAStageBytes + m * 16;
+#pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-          float fwd[16], bwd[16];
-          const int j0 = 32 * q + 16 * half;
-          if (!edge) {
-            // swizzle-128B: 16-byte chunk ch of row m sits at chunk ch ^ (m & 7)
+          // forward elements 16*half .. +15 = x[c + j0 + i].  Backward: x[c - j0 - i] is box element
+          // 32 - 16*half - i; the 16 box elements 16*(1-half) .. +15 give i = 1..15 (reversed) and, in their
+          // first slot, the i = 0 sample of the NEXT half (carried over; the centre sample itself for j = 0).
+          float fwd[16], bwd[16], buf[16];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const float4 f = *reinterpret_cast<const float4*>(fbox + (((4 * half + ch) ^ (m & 7)) << 4));
-              fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
-            }
-            // backward box element e (0..31) = x[c - 32q - 32 + e]; bwd[i] = x[c - j0 - i]:
-            //   half 0: bwd[0] = carry, bwd[i] = box[32 - i]      (i = 1..15)
-            //   half 1: bwd[i] = box[16 - i]                       (i = 0..15)
-            float box[20];
-            const int e0 = half == 0 ? 16 : 0;  // elements e0 .. e0+15 (+ element 16 for half 1)
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const float4 f = *reinterpret_cast<const float4*>(bbox + ((((e0 >> 2) + ch) ^ (m & 7)) << 4));
-              box[4 * ch + 0] = f.x; box[4 * ch + 1] = f.y; box[4 * ch + 2] = f.z; box[4 * ch + 3] = f.w;
-            }
-            if (half == 0) {
-              bwd[0] = (q == 0) ? fwd[0] : carry;
-#pragma unroll
-              for (int i = 1; i < 16; ++i) bwd[i] = box[16 - i];   // element 32 - i = e0 + (16 - i)
-            } else {
-              const float4 f = *reinterpret_cast<const float4*>(bbox + ((4 ^ (m & 7)) << 4));  // elements 16..19
-              bwd[0] = f.x;                                                                     // element 16
-#pragma unroll
-              for (int i = 1; i < 16; ++i) bwd[i] = box[16 - i];   // element 16 - i
-              carry = box[0];                                      // element 0 = x[c - 32q - 32]
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              fwd[i] = valid ? __ldg(x + reflect_idx(c + j0 + i, T)) : 0.0f;
-              bwd[i] = valid ? __ldg(x + reflect_idx(c - j0 - i, T)) : 0.0f;
-            }
+          for (int ch = 0; ch < 4; ++ch) {
+            const float4 f = *reinterpret_cast<const float4*>(fbox + (((4 * half + ch) ^ my_swz) << 4));
+            fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
+            const float4 b = *reinterpret_cast<const float4*>(bbox + (((4 * (1 - half) + ch) ^ my_swz) << 4));
+            buf[4 * ch + 0] = b.x; buf[4 * ch + 1] = b.y; buf[4 * ch + 2] = b.z; buf[4 * ch + 3] = b.w;
           }
+          bwd[0] = (q == 0 && half == 0) ? fwd[0] : carry;
+#pragma unroll
+          for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
+          carry = buf[0];
           fe_u4 chunk[8];
-          fe_gemm_produce_half(fwd, bwd, scale, j0, mid_re_w, mid_im_w, mid_re, mid_im, chunk);
+          fe_gemm_produce_half(fwd, bwd, scale, 32 * q + 16 * half, mid_re_w, mid_im_w, mid_re, mid_im, chunk);
 #pragma unroll
           for (int sf = 0; sf < 8; ++sf) {
-            *reinterpret_cast<fe_u4*>(a_stage + sf * fe_gemm_tile_bytes(kTileM) + fe_gemm_operand_offset(kTileM, m, 8 * half)) = chunk[sf];
+            *reinterpret_cast<fe_u4*>(a_row + sf * fe_gemm_tile_bytes(kTileM) + half * kTileM * 16) = chunk[sf];
           }
         }
         if (q == a.nstages - 1) {
-          s_unscale[pb * kTileM + m] = unscale;
+          s_unscale[pb * kTileM + m] = unscale * unscale;
           s_p128[pb * kTileM + m] = fmaf(mid_re, mid_re, mid_im * mid_im);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_A_FULL + s));
+        if (warp == kProducerWarp0 && lane == 0) FE_TRACE(2, it, q);
+        if (lane == 0) {
+          mbar_arrive(bar(BAR_A_FULL + s));
+          // cells were consumed at the top of the tile, the side buffers are read at every stage
+          if (q == a.nstages - 1) mbar_arrive(bar(BAR_SCOUT_EMPTY + pb));
+        }
       }
     }
-  } else if (warp >= kEpilogueWarp0) {
-    // ================================ epilogue ========================================================
+  } else {
+    // ================================ epilogue (warps 8..15) ==========================================
     const int ew = warp - kEpilogueWarp0;
     const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are the ones this warp may read
     const int grp = ew >> 2;               // column half
     const int m = quarter * 32 + lane;
     const int kper = a.nhalf / 2;
     const int k_begin = grp * kper, k_end = k_begin + kper;
-    const int etid = (warp - kEpilogueWarp0) * 32 + lane;
+    const int etid = ew * 32 + lane;
     const int nfil = a.n_filter;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -407,15 +466,19 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
       const int valid_rows = min(kTileM, a.n_frames - t0);
       mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 8);
       tc_fence_after();
-      const float us = s_unscale[pb * kTileM + m];
+      if (ew == 0 && lane == 0) FE_TRACE(4, it, 0);
+      const float us2 = s_unscale[pb * kTileM + m];
       const float p_mid = s_p128[pb * kTileM + m];
-      float* ecol = s_energy + m;
+      // each column group sums into its own [filter][frame] array (the two groups meet on the filters
+      // around their boundary); a thread only ever touches its own frame's column, so plain updates do
+      float* ecol = s_energy + grp * nfil * kTileM + m;
       auto emit = [&](int f, float v) {
-        if (f >= 0 && f < nfil && v != 0.0f) atomicAdd(ecol + f * kTileM, v * us * us);
+        if (f >= 0 && f < nfil) ecol[f * kTileM] += v * us2;
       };
       fe_gemm_epi_state st;
       fe_gemm_epi_init(st, s_fb[k_begin]);
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
       for (int k0 = k_begin; k0 < k_end; k0 += 16) {
         float ce[16], co[16], se[16], so[16];
         tmem_ld16(tbase + (uint32_t)(0 * a.nhalf + k0), ce);
@@ -424,19 +487,20 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
         tmem_ld16(tbase + (uint32_t)(3 * a.nhalf + k0), so);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) fe_gemm_epi_bin(st, s_fb[k0 + i], ce[i], co[i], se[i], so[i], emit);
+        for (int i = 0; i < 16; ++i)
+          fe_gemm_epi_bin(st, s_fb[k0 + i], (k0 + i) != k_begin, ce[i], co[i], se[i], so[i], emit);
       }
       // accumulators are in registers now: hand TMEM back to the MMA warp
       tc_fence_before();
       __syncwarp();
+      if (ew == 0 && lane == 0) FE_TRACE(5, it, 0);
       if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY));
       fe_gemm_epi_flush(st, emit);
       if (grp == 1) {
         // bin n_fft/4, evaluated by the producer in true units
         const fe_gemm_fb_entry tm = s_fb[a.nhalf];
-        const float p = p_mid;
-        if (tm.phi_lo >= 0 && tm.phi_lo < nfil) atomicAdd(ecol + tm.phi_lo * kTileM, p * tm.w_lo_a);
-        if (tm.phi_lo + 1 >= 0 && tm.phi_lo + 1 < nfil) atomicAdd(ecol + (tm.phi_lo + 1) * kTileM, p * tm.w_lo_b);
+        if (tm.phi_lo >= 0 && tm.phi_lo < nfil) ecol[tm.phi_lo * kTileM] += p_mid * tm.w_lo_a;
+        if (tm.phi_lo + 1 >= 0 && tm.phi_lo + 1 < nfil) ecol[(tm.phi_lo + 1) * kTileM] += p_mid * tm.w_lo_b;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // all emissions of the tile are in s_energy
       // coalesced store: consecutive threads -> consecutive frames of one filter
@@ -444,8 +508,9 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
       float vmax = 0.0f;
       for (int i = etid; i < nfil * kTileM; i += kNumEpilogueWarps * 32) {
         const int f = i >> 7, r = i & (kTileM - 1);
-        const float v = s_energy[i];
+        const float v = s_energy[i] + s_energy[nfil * kTileM + i];
         s_energy[i] = 0.0f;
+        s_energy[nfil * kTileM + i] = 0.0f;
         if (r < valid_rows) {
           dst[(size_t)f * a.n_frames + r] = v;
           vmax = fmaxf(vmax, v);
@@ -456,6 +521,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
         if (lane == 0) atomicMax(a.group_max + (a.row_base + row_local) / a.top_db_group, __float_as_uint(vmax));
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // s_energy is zero again before the next tile emits
+      if (ew == 0 && lane == 0) FE_TRACE(6, it, 0);
     }
   }
 
@@ -507,7 +573,7 @@ bool fe_gemm_auto_prefers(const b200fe_params* p) { return fe_gemm_supported(p) 
 
 int64_t fe_gemm_workspace_bytes(const b200fe_params* p, int64_t chunk_rows, int64_t T) {
   (void)p; (void)chunk_rows; (void)T;
-  return 256;  // error flag
+  return 65536;  // error flag (+ trace buffer in FE_GEMM_TRACE builds)
 }
 
 cudaError_t fe_gemm_launch(const b200fe_params* p, const fe_fft_args& fa, int64_t row_base, int64_t rows,
@@ -517,7 +583,7 @@ cudaError_t fe_gemm_launch(const b200fe_params* p, const fe_fft_args& fa, int64_
   if (!enc) return cudaErrorNotSupported;
   const int hop = p->hop_length;
   const int64_t T = fa.T;
-  const int nb_full = (int)(T / hop);
+  const int nb_map = (int)((T - 1) / hop);  // hop blocks b whose column `hop` (= first sample of block b+1) exists
   gemm_args a;
   a.wave = fa.wave;
   a.tables = fa.tables;
@@ -536,11 +602,11 @@ cudaError_t fe_gemm_launch(const b200fe_params* p, const fe_fft_args& fa, int64_
   a.tiles_per_row = (fa.n_frames + kTileM - 1) / kTileM;
   a.n_tiles = (int32_t)(rows * a.tiles_per_row);
   a.top_db_group = fa.top_db_group;
-  a.nb_full = nb_full;
+  a.nb_map = nb_map;
 
-  // 3-D tensor map over the chunk's rows: [hop samples][nb_full hop blocks][rows]; box 32 x 128 x 1, swizzle 128B
+  // 3-D tensor map over the chunk's rows: [hop samples][nb_map hop blocks][rows]; box 32 x 128 x 1, swizzle 128B
   CUtensorMap map;
-  const cuuint64_t gdim[3] = {(cuuint64_t)hop, (cuuint64_t)nb_full, (cuuint64_t)rows};
+  const cuuint64_t gdim[3] = {(cuuint64_t)hop, (cuuint64_t)nb_map, (cuuint64_t)rows};
   const cuuint64_t gstride[2] = {(cuuint64_t)hop * 4, (cuuint64_t)T * 4};
   const cuuint32_t box[3] = {32, (cuuint32_t)kTileM, 1};
   const cuuint32_t estride[3] = {1, 1, 1};
@@ -550,8 +616,9 @@ cudaError_t fe_gemm_launch(const b200fe_params* p, const fe_fft_args& fa, int64_
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
-  const smem_layout L = make_layout(a.nhalf, a.kpairs);
+  const smem_layout L = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map);
   const int smem = L.total + 1024;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static int attr_done = 0;
   if (attr_done < smem) {
     cudaError_t e = cudaFuncSetAttribute(fe_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -563,6 +630,9 @@ cudaError_t fe_gemm_launch(const b200fe_params* p, const fe_fft_args& fa, int64_
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
   cudaError_t e = cudaMemsetAsync(a.error_flag, 0, 4, stream);
+#ifdef FE_GEMM_TRACE
+  cudaMemsetAsync(a.error_flag, 0, 65536, stream);
+#endif
   if (e != cudaSuccess) return e;
   // the kernel addresses wave relative to the chunk: rows are local to the tensor map
   gemm_args b = a;

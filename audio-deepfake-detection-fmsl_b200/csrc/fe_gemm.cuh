@@ -118,26 +118,33 @@ FE_HD void fe_gemm_epi_init(fe_gemm_epi_state& st, const fe_gemm_fb_entry& first
   st.phi_hi = first.phi_hi;
 }
 
+// One GEMM column k: bins k (ascending window) and n_fft/2 - k (descending window).  A window moves by
+// at most one filter per bin (checked by the host packer); the moves are rare and uniform across
+// threads, so they sit behind one branch; the finished filter sum goes out through emit(filter, value).
+// `allow_move` is 0 for the first column a thread handles (its state was initialised from its phi).
 template <class Emit>
-FE_HD void fe_gemm_epi_bin(fe_gemm_epi_state& st, const fe_gemm_fb_entry& t, float ce, float co, float se, float so,
-                           Emit&& emit) {
+FE_HD void fe_gemm_epi_bin(fe_gemm_epi_state& st, const fe_gemm_fb_entry& t, int allow_move, float ce, float co,
+                           float se, float so, Emit&& emit) {
   const float re1 = ce + co, im1 = se + so, re2 = ce - co, im2 = so - se;
   const float p1 = fmaf(re1, re1, im1 * im1);  // |X[k]|^2           (scaled units)
   const float p2 = fmaf(re2, re2, im2 * im2);  // |X[n_fft/2 - k]|^2
-  while (st.phi_lo < t.phi_lo) {
-    emit(st.phi_lo, st.lo0);
-    st.lo0 = st.lo1;
-    st.lo1 = 0.0f;
-    ++st.phi_lo;
+  const int mv = allow_move ? t.adv : 0;
+  if (mv != 0) {
+    if (mv & 1) {
+      emit(st.phi_lo, st.lo0);
+      st.lo0 = st.lo1;
+      st.lo1 = 0.0f;
+      ++st.phi_lo;
+    }
+    if (mv & 2) {
+      emit(st.phi_hi + 1, st.hi1);
+      st.hi1 = st.hi0;
+      st.hi0 = 0.0f;
+      --st.phi_hi;
+    }
   }
   st.lo0 = fmaf(p1, t.w_lo_a, st.lo0);
   st.lo1 = fmaf(p1, t.w_lo_b, st.lo1);
-  while (st.phi_hi > t.phi_hi) {
-    emit(st.phi_hi + 1, st.hi1);
-    st.hi1 = st.hi0;
-    st.hi0 = 0.0f;
-    --st.phi_hi;
-  }
   st.hi0 = fmaf(p2, t.w_hi_a, st.hi0);
   st.hi1 = fmaf(p2, t.w_hi_b, st.hi1);
 }

@@ -27,7 +27,9 @@ struct alignas(16) fe_gemm_fb_entry {
   float w_lo_a, w_lo_b;   // weights of bin k for filters phi_lo, phi_lo + 1
   float w_hi_a, w_hi_b;   // weights of bin n_fft/2 - k for filters phi_hi, phi_hi + 1
   int32_t phi_lo, phi_hi;
-  int32_t pad0, pad1;
+  int32_t adv;            // bit 0: the ascending window moves up one filter before this bin (k > 0)
+                          // bit 1: the descending window moves down one filter before this bin (k > 0)
+  int32_t pad0;
 };
 
 // UMMA K-major, no-swizzle operand tile of `rows` rows x 16 K-values (one K=16 MMA step):

@@ -100,6 +100,12 @@ int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* win
     fb[k].w_hi_b = fbw(bh, phi[bh] + 1);
     fb[k].phi_lo = phi[bl];
     fb[k].phi_hi = phi[bh];
+    const int adv_lo = k > 0 ? phi[bl] - phi[bl - 1] : 0;
+    const int adv_hi = k > 0 ? phi[bh + 1] - phi[bh] : 0;
+    // the kernel's sweep moves a window by at most one filter per bin
+    if (adv_lo < 0 || adv_lo > 1 || adv_hi < 0 || adv_hi > 1) { h->gemm_ok = 0; return B200FE_OK; }
+    fb[k].adv = adv_lo | (adv_hi << 1);
+    fb[k].pad0 = 0;
   }
   // ---- bin n_fft/4 (handled on the CUDA cores): true-unit weights ------------------------------
   float* mid = (float*)(base + h->off_gemm_mid);

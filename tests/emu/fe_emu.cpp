@@ -212,14 +212,14 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
       for (int m = 0; m < M; ++m) {
         const float us = unscale[m];
         auto emit = [&](int f, float v) {
-          if (f >= 0 && f < nfil && v != 0.0f) E[(size_t)f * M + m] += v * us * us;
+          if (f >= 0 && f < nfil) E[(size_t)f * M + m] += v * (us * us);
         };
         for (int grp = 0; grp < 2; ++grp) {
           const int kper = nhalf / 2, k_begin = grp * kper, k_end = k_begin + kper;
           fe_gemm_epi_state st;
           fe_gemm_epi_init(st, fb[k_begin]);
           for (int k = k_begin; k < k_end; ++k)
-            fe_gemm_epi_bin(st, fb[k], D[((size_t)0 * M + m) * nhalf + k], D[((size_t)1 * M + m) * nhalf + k],
+            fe_gemm_epi_bin(st, fb[k], k != k_begin, D[((size_t)0 * M + m) * nhalf + k], D[((size_t)1 * M + m) * nhalf + k],
                             D[((size_t)2 * M + m) * nhalf + k], D[((size_t)3 * M + m) * nhalf + k], emit);
           fe_gemm_epi_flush(st, emit);
         }
