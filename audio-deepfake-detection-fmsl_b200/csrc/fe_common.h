@@ -43,8 +43,8 @@ struct fe_blob_header {
   int32_t gemm_nhalf;      // n_fft/4 : GEMM N (bins 0 .. n_fft/4-1; bin n_fft/4 handled apart)
   int32_t off_gemm_b;      // __half operand tiles, see fe_gemm.cuh
   int32_t gemm_b_bytes;
-  int32_t off_gemm_fb;     // fe_gemm_fb_entry[gemm_nhalf + 1] sliding filterbank table (fe_gemm_layout.h)
-  int32_t off_gemm_fbflag; // unused
+  int32_t off_gemm_fb;     // fe_gemm_fbw[gemm_nhalf] chunk-local filterbank weights (fe_gemm_layout.h)
+  int32_t off_gemm_fbflag; // fe_gemm_fbctl
   int32_t off_gemm_mid;    // float[2][gemm_kpairs]  true-unit weights of bin n_fft/4 (Re from a_e, Im from a_o)
   int32_t reserved[8];
 };

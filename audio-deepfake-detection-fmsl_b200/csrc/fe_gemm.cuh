@@ -105,56 +105,26 @@ FE_HD void fe_gemm_produce_half(const float* fwd, const float* bwd, float scale,
   }
 }
 
-// ---- epilogue: power of bins k and n_fft/2 - k from the four accumulators, swept through the
-// triangular filterbank with two sliding windows (ascending bins k, descending bins n_fft/2 - k) ----
-struct fe_gemm_epi_state {
-  float lo0, lo1, hi0, hi1;
-  int phi_lo, phi_hi;
-};
-
-FE_HD void fe_gemm_epi_init(fe_gemm_epi_state& st, const fe_gemm_fb_entry& first) {
-  st.lo0 = st.lo1 = st.hi0 = st.hi1 = 0.0f;
-  st.phi_lo = first.phi_lo;
-  st.phi_hi = first.phi_hi;
-}
-
-// One GEMM column k: bins k (ascending window) and n_fft/2 - k (descending window).  A window moves by
-// at most one filter per bin (checked by the host packer); the moves are rare and uniform across
-// threads, so they sit behind one branch; the finished filter sum goes out through emit(filter, value).
-// `allow_move` is 0 for the first column a thread handles (its state was initialised from its phi).
-template <class Emit>
-FE_HD void fe_gemm_epi_bin(fe_gemm_epi_state& st, const fe_gemm_fb_entry& t, int allow_move, float ce, float co,
-                           float se, float so, Emit&& emit) {
-  const float re1 = ce + co, im1 = se + so, re2 = ce - co, im2 = so - se;
-  const float p1 = fmaf(re1, re1, im1 * im1);  // |X[k]|^2           (scaled units)
-  const float p2 = fmaf(re2, re2, im2 * im2);  // |X[n_fft/2 - k]|^2
-  const int mv = allow_move ? t.adv : 0;
-  if (mv != 0) {
-    if (mv & 1) {
-      emit(st.phi_lo, st.lo0);
-      st.lo0 = st.lo1;
-      st.lo1 = 0.0f;
-      ++st.phi_lo;
-    }
-    if (mv & 2) {
-      emit(st.phi_hi + 1, st.hi1);
-      st.hi1 = st.hi0;
-      st.hi0 = 0.0f;
-      --st.phi_hi;
+// ---- epilogue: NB consecutive GEMM columns of one 16-column chunk.  Powers of bins k and n_fft/2 - k
+// from the four accumulators (ce+co, se+so | ce-co, so-se), then 4 chunk-local filter sums per bin run
+// with dense weights (fe_gemm_layout.h): 8 flops + 8 FMAs per column, no data-dependent control flow.
+// The caller zeroes acc_lo / acc_hi at the start of a chunk and adds them to the frame's filter sums at
+// its end; the body is kept small (NB = 8) so the loop stays resident in the instruction cache.
+template <int NB>
+FE_HD void fe_gemm_epi_cols(const fe_gemm_fbw* w, const float* ce, const float* co, const float* se,
+                            const float* so, float* acc_lo, float* acc_hi) {
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const float re1 = ce[i] + co[i], im1 = se[i] + so[i], re2 = ce[i] - co[i], im2 = so[i] - se[i];
+    const float p1 = fmaf(re1, re1, im1 * im1);  // |X[k]|^2           (scaled units)
+    const float p2 = fmaf(re2, re2, im2 * im2);  // |X[n_fft/2 - k]|^2
+    const fe_gemm_fbw t = w[i];
+#pragma unroll
+    for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) {
+      acc_lo[j] = fmaf(p1, t.lo[j], acc_lo[j]);
+      acc_hi[j] = fmaf(p2, t.hi[j], acc_hi[j]);
     }
   }
-  st.lo0 = fmaf(p1, t.w_lo_a, st.lo0);
-  st.lo1 = fmaf(p1, t.w_lo_b, st.lo1);
-  st.hi0 = fmaf(p2, t.w_hi_a, st.hi0);
-  st.hi1 = fmaf(p2, t.w_hi_b, st.hi1);
-}
-
-template <class Emit>
-FE_HD void fe_gemm_epi_flush(fe_gemm_epi_state& st, Emit&& emit) {
-  emit(st.phi_lo, st.lo0);
-  emit(st.phi_lo + 1, st.lo1);
-  emit(st.phi_hi, st.hi0);
-  emit(st.phi_hi + 1, st.hi1);
 }
 
 #endif  // FE_GEMM_CUH_

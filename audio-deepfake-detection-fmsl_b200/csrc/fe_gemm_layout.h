@@ -22,14 +22,23 @@
 #define FE_GEMM_A_SCALE_LOG2 13   // per frame: 2*max|x| is scaled into [2^13, 2^14)
 #define FE_GEMM_STAGE_J 32        // sample pairs per pipeline stage: one K=16 MMA step per sub-GEMM
 
-// sliding triangular-filterbank table, one entry per GEMM column k (bins k and n_fft/2 - k)
-struct alignas(16) fe_gemm_fb_entry {
-  float w_lo_a, w_lo_b;   // weights of bin k for filters phi_lo, phi_lo + 1
-  float w_hi_a, w_hi_b;   // weights of bin n_fft/2 - k for filters phi_hi, phi_hi + 1
-  int32_t phi_lo, phi_hi;
-  int32_t adv;            // bit 0: the ascending window moves up one filter before this bin (k > 0)
-                          // bit 1: the descending window moves down one filter before this bin (k > 0)
-  int32_t pad0;
+// Filterbank tables of the epilogue.  GEMM column k carries bins k ("lo") and n_fft/2 - k ("hi").  Within
+// a chunk of 16 consecutive columns each of the two bin runs may only touch FE_GEMM_FB_SPAN consecutive
+// filters (true for triangular banks whose filters are at least 8 bins apart; checked by the packer), so a
+// thread accumulates each run into 4 chunk-local sums with dense weights — straight-line code, no
+// data-dependent control flow — and adds them to the per-frame filter sums once per chunk.
+#define FE_GEMM_FB_SPAN 4
+#define FE_GEMM_CHUNK 16
+struct alignas(16) fe_gemm_fbw {
+  float lo[FE_GEMM_FB_SPAN];  // weights of bin k for filters base_lo[chunk] + 0..3
+  float hi[FE_GEMM_FB_SPAN];  // weights of bin n_fft/2 - k for filters base_hi[chunk] + 0..3
+};
+// control block: first filter of each chunk's runs, and bin n_fft/4 (evaluated apart) as up to 4 filters
+struct fe_gemm_fbctl {
+  int32_t base_lo[16], base_hi[16];   // per chunk (nhalf / 16 <= 8 used)
+  int32_t mid_base;
+  float mid_w[FE_GEMM_FB_SPAN];
+  int32_t pad[3];
 };
 
 // UMMA K-major, no-swizzle operand tile of `rows` rows x 16 K-values (one K=16 MMA step):

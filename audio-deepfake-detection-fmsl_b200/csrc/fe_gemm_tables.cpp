@@ -48,7 +48,9 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
   h->gemm_b_bytes = g.nstages * fe_gemm_b_stage_bytes(g.nhalf);
   off = fe_align16(off + h->gemm_b_bytes);
   h->off_gemm_fb = (int32_t)off;
-  off = fe_align16(off + (int64_t)(g.nhalf + 1) * sizeof(fe_gemm_fb_entry));
+  off = fe_align16(off + (int64_t)g.nhalf * sizeof(fe_gemm_fbw));
+  h->off_gemm_fbflag = (int32_t)off;
+  off = fe_align16(off + (int64_t)sizeof(fe_gemm_fbctl));
   h->off_gemm_mid = (int32_t)off;
   off = fe_align16(off + (int64_t)2 * g.kpairs * 4);
   h->gemm_ok = 1;  // provisional: fe_gemm_pack clears it when the window / filterbank do not qualify
@@ -73,39 +75,41 @@ int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* win
     if (fabs(a - b) > 1e-6 * wmax) { h->gemm_ok = 0; return B200FE_OK; }
     wj[j] = 0.5 * (a + b);
   }
-  // ---- filterbank structure: every bin feeds at most two adjacent filters, monotonically ---------
-  std::vector<int> phi(n_freq);
-  int cur = -1;
-  for (int b = 0; b < n_freq; ++b) {
-    int first = -1, last = -1, cnt = 0;
-    for (int f = 0; f < nfil; ++f)
-      if (fbank[(int64_t)b * nfil + f] != 0.0f) { if (first < 0) first = f; last = f; ++cnt; }
-    if (cnt == 0) { phi[b] = cur; continue; }
-    if (last - first > 1 || cnt > 2) { h->gemm_ok = 0; return B200FE_OK; }
-    int want;
-    if (cnt == 2) want = first;
-    else want = (cur < first - 1) ? first - 1 : (cur > first ? -2 : cur);  // keep cur if it still covers `first`
-    if (want == -2 || want < cur) { h->gemm_ok = 0; return B200FE_OK; }
-    cur = want;
-    phi[b] = cur;
-  }
-  auto fbw = [&](int b, int f) -> float { return (f >= 0 && f < nfil) ? fbank[(int64_t)b * nfil + f] : 0.0f; };
-  fe_gemm_fb_entry* fb = (fe_gemm_fb_entry*)(base + h->off_gemm_fb);
+  // ---- filterbank: per 16-column chunk, each bin run touches at most 4 consecutive filters ----------
+  fe_gemm_fbw* fbw = (fe_gemm_fbw*)(base + h->off_gemm_fb);
+  fe_gemm_fbctl* ctl = (fe_gemm_fbctl*)(base + h->off_gemm_fbflag);
+  memset(ctl, 0, sizeof(*ctl));
   const int nyq = n_fft / 2;
-  for (int k = 0; k <= g.nhalf; ++k) {
-    const int bl = k, bh = nyq - k;
-    fb[k].w_lo_a = fbw(bl, phi[bl]);
-    fb[k].w_lo_b = fbw(bl, phi[bl] + 1);
-    fb[k].w_hi_a = fbw(bh, phi[bh]);
-    fb[k].w_hi_b = fbw(bh, phi[bh] + 1);
-    fb[k].phi_lo = phi[bl];
-    fb[k].phi_hi = phi[bh];
-    const int adv_lo = k > 0 ? phi[bl] - phi[bl - 1] : 0;
-    const int adv_hi = k > 0 ? phi[bh + 1] - phi[bh] : 0;
-    // the kernel's sweep moves a window by at most one filter per bin
-    if (adv_lo < 0 || adv_lo > 1 || adv_hi < 0 || adv_hi > 1) { h->gemm_ok = 0; return B200FE_OK; }
-    fb[k].adv = adv_lo | (adv_hi << 1);
-    fb[k].pad0 = 0;
+  auto span_of = [&](int b_first, int b_last, int* lo_f, int* hi_f) {  // filters with weight on bins b_first..b_last
+    *lo_f = nfil; *hi_f = -1;
+    for (int b = b_first; b <= b_last; ++b)
+      for (int f = 0; f < nfil; ++f)
+        if (fbank[(int64_t)b * nfil + f] != 0.0f) { if (f < *lo_f) *lo_f = f; if (f > *hi_f) *hi_f = f; }
+  };
+  for (int c = 0; c < g.nhalf / FE_GEMM_CHUNK; ++c) {
+    const int k0 = c * FE_GEMM_CHUNK, k1 = k0 + FE_GEMM_CHUNK - 1;
+    int f0, f1;
+    span_of(k0, k1, &f0, &f1);
+    if (f1 >= 0 && f1 - f0 >= FE_GEMM_FB_SPAN) { h->gemm_ok = 0; return B200FE_OK; }
+    const int bl = f1 < 0 ? 0 : f0;
+    span_of(nyq - k1, nyq - k0, &f0, &f1);
+    if (f1 >= 0 && f1 - f0 >= FE_GEMM_FB_SPAN) { h->gemm_ok = 0; return B200FE_OK; }
+    const int bh = f1 < 0 ? 0 : f0;
+    ctl->base_lo[c] = bl;
+    ctl->base_hi[c] = bh;
+    for (int k = k0; k <= k1; ++k)
+      for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) {
+        fbw[k].lo[j] = (bl + j < nfil) ? fbank[(int64_t)k * nfil + bl + j] : 0.0f;
+        fbw[k].hi[j] = (bh + j < nfil) ? fbank[(int64_t)(nyq - k) * nfil + bh + j] : 0.0f;
+      }
+  }
+  {
+    int f0, f1;
+    span_of(g.nhalf, g.nhalf, &f0, &f1);
+    if (f1 >= 0 && f1 - f0 >= FE_GEMM_FB_SPAN) { h->gemm_ok = 0; return B200FE_OK; }
+    ctl->mid_base = f1 < 0 ? 0 : f0;
+    for (int j = 0; j < FE_GEMM_FB_SPAN; ++j)
+      ctl->mid_w[j] = (f1 >= 0 && f0 + j < nfil) ? fbank[(int64_t)g.nhalf * nfil + f0 + j] : 0.0f;
   }
   // ---- bin n_fft/4 (handled on the CUDA cores): true-unit weights ------------------------------
   float* mid = (float*)(base + h->off_gemm_mid);

@@ -235,6 +235,11 @@ class FrontEndEngine:
             if offsets.device != dev or lengths.device != dev:
                 raise ValueError("offsets / lengths must be on the waveform's device")
         p = self._params_with_group(group)
+        if offsets is not None and self.requested_variant == "auto" and p.variant != _lib.VARIANT_FFT:
+            # ragged (repeat-pad) input is implemented by the FFT variant only; AUTO may switch, an explicit
+            # variant request may not (the library then reports "unsupported")
+            p = _lib.Params.from_buffer_copy(p)
+            p.variant = _lib.VARIANT_FFT
         nf = self.n_frames(T)
         if out is None:
             out = torch.empty((R, self.n_out, nf), dtype=torch.float32, device=dev)

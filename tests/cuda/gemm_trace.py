@@ -24,3 +24,5 @@ for it in range(6):
     for q in range(5):
         print("  q", q, {names[e]: int(tr[it, q, e] - base) for e in range(4)})
     print("   ", {names[e]: int(tr[it, 0, e] - base) for e in range(4, 8)})
+    print("    scout start/done, producer got scout:", [int(tr[it, 0, e] - base) for e in (10, 11, 12)])
+    print("    epi chunks (after ld wait, after bins):", [(int(tr[it, c, 8] - base), int(tr[it, c, 9] - base)) for c in range(4)])

@@ -151,7 +151,8 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
   const int T = (int)T_, hop = p->hop_length, nF = 1 + T / hop, nfil = p->n_filter;
   const int kpairs = h->gemm_kpairs, nhalf = h->gemm_nhalf, nstages = kpairs / 32;
   const int nb_full = T / hop;
-  const fe_gemm_fb_entry* fb = (const fe_gemm_fb_entry*)(blob + h->off_gemm_fb);
+  const fe_gemm_fbw* fbw = (const fe_gemm_fbw*)(blob + h->off_gemm_fb);
+  const fe_gemm_fbctl* ctl = (const fe_gemm_fbctl*)(blob + h->off_gemm_fbflag);
   const float* mid = (const float*)(blob + h->off_gemm_mid);
   const unsigned char* gB = blob + h->off_gemm_b;
   const int M = FE_GEMM_TILE_M;
@@ -208,25 +209,29 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
               D[((size_t)sub * M + m) * nhalf + n] = acc;
             }
       }
-      // epilogue: two column groups per frame
+      // epilogue: per frame, chunks of 16 columns
       for (int m = 0; m < M; ++m) {
-        const float us = unscale[m];
-        auto emit = [&](int f, float v) {
-          if (f >= 0 && f < nfil) E[(size_t)f * M + m] += v * (us * us);
-        };
-        for (int grp = 0; grp < 2; ++grp) {
-          const int kper = nhalf / 2, k_begin = grp * kper, k_end = k_begin + kper;
-          fe_gemm_epi_state st;
-          fe_gemm_epi_init(st, fb[k_begin]);
-          for (int k = k_begin; k < k_end; ++k)
-            fe_gemm_epi_bin(st, fb[k], k != k_begin, D[((size_t)0 * M + m) * nhalf + k], D[((size_t)1 * M + m) * nhalf + k],
-                            D[((size_t)2 * M + m) * nhalf + k], D[((size_t)3 * M + m) * nhalf + k], emit);
-          fe_gemm_epi_flush(st, emit);
+        const float us2 = unscale[m] * unscale[m];
+        for (int c = 0; c < nhalf / FE_GEMM_CHUNK; ++c) {
+          float ce[16], co[16], se[16], so[16], alo[FE_GEMM_FB_SPAN], ahi[FE_GEMM_FB_SPAN];
+          for (int i = 0; i < 16; ++i) {
+            const int k = 16 * c + i;
+            ce[i] = D[((size_t)0 * M + m) * nhalf + k];
+            co[i] = D[((size_t)1 * M + m) * nhalf + k];
+            se[i] = D[((size_t)2 * M + m) * nhalf + k];
+            so[i] = D[((size_t)3 * M + m) * nhalf + k];
+          }
+          for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) alo[j] = ahi[j] = 0.0f;
+          fe_gemm_epi_cols<8>(fbw + 16 * c, ce, co, se, so, alo, ahi);
+          fe_gemm_epi_cols<8>(fbw + 16 * c + 8, ce + 8, co + 8, se + 8, so + 8, alo, ahi);
+          for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) {
+            if (ctl->base_lo[c] + j < nfil) E[(size_t)(ctl->base_lo[c] + j) * M + m] += alo[j] * us2;
+            if (ctl->base_hi[c] + j < nfil) E[(size_t)(ctl->base_hi[c] + j) * M + m] += ahi[j] * us2;
+          }
         }
-        const fe_gemm_fb_entry tm = fb[nhalf];
         const float pmid = mre[m] * mre[m] + mim[m] * mim[m];
-        if (tm.phi_lo >= 0 && tm.phi_lo < nfil) E[(size_t)tm.phi_lo * M + m] += pmid * tm.w_lo_a;
-        if (tm.phi_lo + 1 >= 0 && tm.phi_lo + 1 < nfil) E[(size_t)(tm.phi_lo + 1) * M + m] += pmid * tm.w_lo_b;
+        for (int j = 0; j < FE_GEMM_FB_SPAN; ++j)
+          if (ctl->mid_base + j < nfil) E[(size_t)(ctl->mid_base + j) * M + m] += pmid * ctl->mid_w[j];
       }
       const int valid_rows = std::min(M, nF - t0);
       for (int f = 0; f < nfil; ++f)

@@ -287,3 +287,62 @@ def test_stream_and_graph_capture(fe):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out_g, expect)
+
+
+# ---- variant-specific checks ---------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_fbank_energy_stage(fe, variant):
+    """Stage output (spec^T @ fb)^T of both kernel families against a float64 evaluation."""
+    m = _variant_or_skip(fe, variant)
+    x = np.concatenate([synth.s1_noise(3), synth.s3_edge()[[1, 2, 3]]], 0)
+    ref = O.apply_fbank(O.power_spectrogram(x.astype(np.float64), 512, 320, 160),
+                        O.linear_fbanks(257, 0.0, 8000.0, 20, 16000).astype(np.float64))
+    e = m.engine.fbank_energies(cuda(x)).cpu().numpy()
+    assert e.shape == ref.shape
+    for r in range(x.shape[0]):
+        assert np.abs(e[r] - ref[r]).max() <= 4e-6 * ref[r].max(), (variant, r)
+
+
+@pytest.mark.parametrize("T", [64000, 8000, 4308, 32000])
+def test_dft_gemm_edges_and_short_inputs(fe, T):
+    """T % hop == 0 (two trailing reflect frames), fewer than 128 frames, partial last tiles."""
+    g = _variant_or_skip(fe, "dft_gemm")
+    f = fe.LFCCDelta(**LFCC_CFG, variant="fft")
+    x = synth.s1_noise(5, T, seed=T)
+    a, b = g(cuda(x)).cpu().numpy(), f(cuda(x)).cpu().numpy()
+    ref = LFCCDeltaRef()(torch.from_numpy(x)).numpy()
+    assert a.shape == ref.shape
+    assert_feat_close(a, ref, TOL, f"dft_gemm vs torchaudio, T={T}")
+    assert_feat_close(b, ref, TOL, f"fft vs torchaudio, T={T}")
+
+
+def test_dft_gemm_amplitude_range(fe):
+    """Per-frame fp16 scaling: int16-range and very quiet inputs keep fp32-level relative accuracy."""
+    g = _variant_or_skip(fe, "dft_gemm")
+    x = synth.s1_noise(2, 16000)
+    base = g.engine.fbank_energies(cuda(x)).cpu().numpy()
+    for k in (-30, 15):
+        e = g.engine.fbank_energies(cuda(np.ldexp(x, k).astype(np.float32))).cpu().numpy()
+        assert np.array_equal(e, np.ldexp(base, 2 * k).astype(np.float32))
+
+
+def test_variants_agree_on_config2_sample(fe):
+    """Both kernel families on the same 512-utterance sample of the benchmark workload."""
+    g = _variant_or_skip(fe, "dft_gemm")
+    f = fe.LFCCDelta(**LFCC_CFG, variant="fft")
+    x = cuda(synth.s1_noise(64)).repeat(8, 1)
+    a, b = g(x), f(x)
+    err = ((a - b).abs() / b.abs().clamp_min(1.0)).amax()
+    assert float(err) <= TOL
+    assert torch.equal(a[:64], a[448:])
+
+
+def test_auto_variant_and_explicit_errors(fe):
+    assert fe.LFCCDelta(**LFCC_CFG).engine.resolved_variant() == ("dft_gemm" if fe._lib.load().b200fe_has_tcgen05() else "fft")
+    assert fe.MelSpectrogram(**MEL_CFG, log="db").engine.resolved_variant() == "fft"
+    with pytest.raises(NotImplementedError):
+        fe.MelSpectrogram(**MEL_CFG, variant="dft_gemm")
+    m = fe.LFCCDelta(**LFCC_CFG, variant="dft_gemm")
+    flat, offsets, lengths = synth.s4_ragged(4)
+    with pytest.raises(NotImplementedError):   # ragged input is an FFT-variant feature: no silent switch
+        m.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600)
