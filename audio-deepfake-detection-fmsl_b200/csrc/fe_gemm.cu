@@ -67,8 +67,11 @@ __host__ __device__ inline smem_layout make_layout(int nhalf, int kpairs, int n_
   L.cells = off;     off += 2 * kMaxCells * 4;
   L.side = off;      off += 2 * side_slots * 2 * kpairs * 4;            // 5 KB at 160 pairs, 2 slots
   L.side_max = off;  off += 2 * 4 * 4;
-  L.unscale = off;   off += 2 * kTileM * 4;
-  L.p128 = off;      off += 2 * kTileM * 4;
+  // per-frame 1/scale^2 and |X[n_fft/4]|^2, producer -> epilogue.  With >= 3 stages the producers reach the
+  // last stage of tile i+1 only after the epilogue of tile i has read its copy, so one buffer suffices.
+  const int pe_bufs = (kpairs / FE_GEMM_STAGE_J) >= 3 ? 1 : 2;
+  L.unscale = off;   off += pe_bufs * kTileM * 4;
+  L.p128 = off;      off += pe_bufs * kTileM * 4;
   off = (off + 15) & ~15;
   L.bars = off;      off += 16 * 8;
   L.tmem_slot = off; off += 16;
@@ -207,11 +210,17 @@ __device__ __forceinline__ int edge_slot(int t, int nb_map, int n_frames) {
 __global__ void __launch_bounds__(kThreads, 1)
 fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  // round the dynamic window up to 1024 bytes (swizzled TMA boxes) without leaving the shared address space
-  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  // the swizzled TMA boxes need a 1024-byte aligned window; __align__(1024) on the extern array is honoured
+  // (no static shared memory in this kernel) — checked, not assumed
+  unsigned char* smem = smem_dyn;
+  if ((smem_u32(smem_dyn) & 1023u) != 0u) {
+    if (threadIdx.x == 0) atomicExch(a.error_flag, 99);
+    return;
+  }
 
   const smem_layout L = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map);
   const int side_slots = 1 + a.n_frames - a.nb_map;
+  const int pe_stride = a.nstages >= 3 ? 0 : kTileM;  // see make_layout
   const int side_floats = 2 * a.kpairs;  // per edge slot: forward[kpairs] + backward in box order [kpairs]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
@@ -470,8 +479,8 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
           }
         }
         if (q == a.nstages - 1) {
-          s_unscale[pb * kTileM + m] = unscale * unscale;
-          s_p128[pb * kTileM + m] = fmaf(mid_re, mid_re, mid_im * mid_im);
+          s_unscale[pb * pe_stride + m] = unscale * unscale;
+          s_p128[pb * pe_stride + m] = fmaf(mid_re, mid_re, mid_im * mid_im);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -502,8 +511,8 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
       mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 8);
       tc_fence_after();
       if (ew == 0 && lane == 0) FE_TRACE(4, it, 0);
-      const float us2 = s_unscale[pb * kTileM + m];
-      const float p_mid = s_p128[pb * kTileM + m];
+      const float us2 = s_unscale[pb * pe_stride + m];
+      const float p_mid = s_p128[pb * pe_stride + m];
       // each column group sums into its own [filter][frame] array (the two groups meet on the filters
       // around their boundary); a thread only ever touches its own frame's column, so plain updates do
       float* ecol = s_energy + grp * nfil * kTileM + m;
@@ -661,7 +670,7 @@ cudaError_t fe_gemm_launch(const b200fe_params* p, const fe_fft_args& fa, int64_
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
   const smem_layout L = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map);
-  const int smem = L.total + 1024;
+  const int smem = L.total;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static int attr_done = 0;
   if (attr_done < smem) {

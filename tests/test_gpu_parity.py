@@ -197,11 +197,14 @@ def test_ragged_repeat_pad(fe):
     flat, offsets, lengths = synth.s4_ragged(24)
     lengths[0], lengths[1] = 64600, 64601
     dense = np.stack([O.pad_repeat(flat[o:o + l], 64600) for o, l in zip(offsets, lengths)])
-    m = fe.LFCCDelta(**LFCC_CFG)
+    m = fe.LFCCDelta(**LFCC_CFG, variant="fft")   # the repeat-pad loader lives in the FFT variant
     a = m.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600)
     b = m(cuda(dense))
     assert a.shape == (24, 60, 404)
     assert torch.equal(a, b)
+    # AUTO switches to the FFT variant for ragged input instead of failing
+    auto = fe.LFCCDelta(**LFCC_CFG)
+    assert torch.equal(auto.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600), a)
     ref = LFCCDeltaRef()(torch.from_numpy(dense)).numpy()
     assert_feat_close(a.cpu().numpy(), ref, TOL, "ragged vs torchaudio on pad()-ed clips")
 
