@@ -203,6 +203,120 @@ __global__ void __launch_bounds__(kTailThreads) fe_tail_kernel(fe_tail_args a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fe_tail_fast_kernel : the same arithmetic as fe_tail_kernel (same operation order, so the results
+// are bit-identical) for n_filter, n_coef <= 32, one thread per tile position: the frame's (log)
+// energies and cepstral coefficients live in registers, only the delta stencils go through shared
+// memory.  grid (tiles, rows), block = tt + 2*halo rounded up to a warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastMax = 32;
+
+template <int KQ>  // KQ = ceil(channels / 4): the cepstral coefficients a thread keeps in registers
+__global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
+  constexpr int kRegs = 4 * KQ;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tt = a.tt, halo = a.halo, w = tt + 2 * halo;
+  const int nfil = a.n_filter, ncoef = a.n_coef;
+  const int nc = ncoef > 0 ? ncoef : nfil;
+  float* s_c = reinterpret_cast<float*>(smem_raw);      // [nc][w]
+  float* s_d = s_c + (size_t)nc * w;                    // [nc][w]
+  float* s_dct = s_d + (size_t)nc * w;                  // [nfil][kFastMax] (zero padded rows of 32)
+
+  const int j = threadIdx.x;
+  const int64_t row_local = blockIdx.y;
+  const int64_t row = a.row_base + row_local;
+  const int t0 = blockIdx.x * tt;
+  const int nF = a.n_frames;
+  const int tv0 = t0 - halo;
+  const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
+  const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
+  if (ncoef > 0) {
+    const float* gd = reinterpret_cast<const float*>(blob + h->off_dct);
+    for (int i = j; i < nfil * kFastMax; i += blockDim.x) {
+      const int f = i / kFastMax, k = i - f * kFastMax;
+      s_dct[i] = k < ncoef ? gd[f * ncoef + k] : 0.0f;
+    }
+  }
+  float floor_db = -INFINITY;
+  if (a.log_mode == B200FE_LOG_DB && a.top_db >= 0.0f) {
+    const float gmax = __uint_as_float(a.group_max[row / a.top_db_group]);
+    floor_db = 10.0f * log10f(fmaxf(gmax, 1e-10f)) - a.top_db;
+  }
+  __syncthreads();
+
+  float c[kRegs];
+#pragma unroll
+  for (int k = 0; k < kRegs; ++k) c[k] = 0.0f;
+  if (j < w) {
+    const int t = fe_clampi(tv0 + j, 0, nF - 1);
+    const float* src = a.energies + (size_t)row_local * nfil * nF + t;
+#pragma unroll 4
+    for (int f = 0; f < nfil; ++f) {
+      float v = __ldg(src + (size_t)f * nF);
+      if (a.log_mode == B200FE_LOG_DB) {
+        v = 10.0f * log10f(fmaxf(v, 1e-10f));
+        v = fmaxf(v, floor_db);
+      } else if (a.log_mode == B200FE_LOG_LN) {
+        v = logf(v + 1e-6f);
+      }
+      if (ncoef > 0) {
+        const float4* dr = reinterpret_cast<const float4*>(s_dct + f * kFastMax);
+#pragma unroll
+        for (int k4 = 0; k4 < KQ; ++k4) {
+          const float4 d = dr[k4];
+          c[4 * k4 + 0] = fmaf(v, d.x, c[4 * k4 + 0]);
+          c[4 * k4 + 1] = fmaf(v, d.y, c[4 * k4 + 1]);
+          c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
+          c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
+        }
+      } else {
+        // no DCT: channel f is the (log) energy itself; unrolled select keeps c[] in registers
+#pragma unroll
+        for (int k = 0; k < kRegs; ++k) c[k] = (k == f) ? v : c[k];
+      }
+    }
+    if (a.deltas >= 1) {
+#pragma unroll
+      for (int k = 0; k < kRegs; ++k)
+        if (k < nc) s_c[(size_t)k * w + j] = c[k];
+    }
+  }
+  const int n = (a.delta_win - 1) / 2;
+  const float denom = (float)(n * (n + 1) * (2 * n + 1)) / 3.0f;
+  const bool owner = j >= halo && j < halo + tt && (t0 + j - halo) < nF;   // this thread stores frame t0 + j - halo
+  float* out_row = a.out + (size_t)row * a.n_out * nF + (t0 + j - halo);
+  if (owner) {
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k)
+      if (k < nc) out_row[(size_t)k * nF] = c[k];
+  }
+  if (a.deltas >= 1) {
+    __syncthreads();
+    const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;   // tile position of the clamped frame
+    if (j >= n && j < w - n) {
+      for (int k = 0; k < nc; ++k) {
+        const float* cc = s_c + (size_t)k * w + tcl;
+        float acc = 0.0f;
+        for (int m = -n; m <= n; ++m) acc += (float)m * cc[m];
+        const float d = acc / denom;
+        s_d[(size_t)k * w + j] = d;
+        if (owner) out_row[(size_t)(nc + k) * nF] = d;
+      }
+    }
+    if (a.deltas >= 2) {
+      __syncthreads();
+      if (owner) {
+        for (int k = 0; k < nc; ++k) {
+          const float* dd = s_d + (size_t)k * w + j;
+          float acc = 0.0f;
+          for (int m = -n; m <= n; ++m) acc += (float)m * dd[m];
+          out_row[(size_t)(2 * nc + k) * nF] = acc / denom;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fe_cmvn_kernel : one warp per (row, channel); in place
 // ------------------------------------------------------------------------------------------------
 __global__ void fe_cmvn_kernel(float* out, int64_t n_series, int n_frames, float eps) {
@@ -297,7 +411,38 @@ size_t fe_tail_smem_bytes(const fe_tail_args& a) {
   return fl * 4;
 }
 
+static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cudaStream_t stream) {
+  fe_tail_args a = a_in;
+  // tile so that tt + 2*halo fills (almost) a whole number of warps, at most 256 threads
+  const int max_tt = 256 - 2 * a.halo;
+  const int tiles = (a.n_frames + max_tt - 1) / max_tt;
+  a.tt = (a.n_frames + tiles - 1) / tiles;
+  const int w = a.tt + 2 * a.halo;
+  const int threads = (w + 31) & ~31;
+  const int nc = a.n_coef > 0 ? a.n_coef : a.n_filter;
+  const size_t smem = ((size_t)2 * nc * w + (size_t)a.n_filter * kFastMax) * 4;
+  typedef void (*kern_t)(fe_tail_args);
+  static const kern_t kerns[8] = {fe_tail_fast_kernel<1>, fe_tail_fast_kernel<2>, fe_tail_fast_kernel<3>,
+                                  fe_tail_fast_kernel<4>, fe_tail_fast_kernel<5>, fe_tail_fast_kernel<6>,
+                                  fe_tail_fast_kernel<7>, fe_tail_fast_kernel<8>};
+  const kern_t kern = kerns[(nc + 3) / 4 - 1];
+  cudaError_t e = set_smem((const void*)kern, smem);
+  if (e != cudaSuccess) return e;
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+    fe_tail_args b = a;
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    b.row_base = a.row_base + r0;
+    b.energies = a.energies + (size_t)r0 * a.n_filter * a.n_frames;
+    dim3 grid((unsigned)tiles, (unsigned)nr);
+    kern<<<grid, threads, smem, stream>>>(b);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t fe_launch_tail(const fe_tail_args& a, int64_t rows, cudaStream_t stream) {
+  if (a.n_filter <= kFastMax && a.n_coef <= kFastMax && !a.force_generic) return launch_tail_fast(a, rows, stream);
   const size_t smem = fe_tail_smem_bytes(a);
   cudaError_t e = set_smem((const void*)fe_tail_kernel, smem);
   if (e != cudaSuccess) return e;

@@ -349,3 +349,22 @@ def test_auto_variant_and_explicit_errors(fe):
     flat, offsets, lengths = synth.s4_ragged(4)
     with pytest.raises(NotImplementedError):   # ragged input is an FFT-variant feature: no silent switch
         m.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600)
+
+
+def test_fast_tail_equals_generic_tail(fe, monkeypatch):
+    """fe_tail_fast_kernel (registers) and fe_tail_kernel (the one the CPU emulation covers) perform the
+    same operations in the same order: identical bits."""
+    x = cuda(np.concatenate([synth.s1_noise(6), synth.s3_edge()], 0))
+    for kw in (dict(deltas=2), dict(deltas=1), dict(deltas=0), dict(deltas=2, log_lf=True)):
+        m = fe.LFCC(**LFCC_CFG, variant="fft", **kw)
+        monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
+        fast = m(x).clone()
+        monkeypatch.setenv("B200FE_GENERIC_TAIL", "1")
+        generic = m(x).clone()
+        monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
+        assert torch.equal(fast, generic), kw
+    short = cuda(synth.s1_noise(3, 4000))
+    m = fe.LFCCDelta(**LFCC_CFG, variant="fft")
+    fast = m(short).clone()
+    monkeypatch.setenv("B200FE_GENERIC_TAIL", "1")
+    assert torch.equal(fast, m(short))
