@@ -5,12 +5,12 @@
 //   tcgen05.ld --epilogue warps (power, sliding triangular filterbank)--> filterbank energies
 //
 // One persistent CTA per SM walks over tiles of 128 frames of one utterance.  Warp roles:
-//   warp 0  loader   TMA tensor-map boxes of samples + cp.async.bulk of the DFT operand stage
-//   warp 1  MMA      one elected thread issues tcgen05.mma / tcgen05.commit
-//   warp 2  scout    per-hop-block max|x| of the next tile (per-frame power-of-two scale), L2 prefetch
-//   warp 3  idle
-//   warps 4-7   producers, lane <-> frame (TMEM lane): folded samples -> UMMA K-major A tiles
-//   warps 8-15  epilogue, lane <-> frame; two warps per TMEM lane quarter split the columns
+//   warps 0-7   epilogue, lane <-> frame; two warps per TMEM lane quarter split the columns
+//   warps 8-15  producers, lane <-> frame (TMEM lane): folded samples -> UMMA K-major A tiles; warps 8-11 take
+//               the first 16 sample pairs of a stage, warps 12-15 the other 16
+//   warp 16     loader: TMA tensor-map boxes of samples + cp.async.bulk of the DFT operand stage
+//   warp 17     MMA: one elected thread issues tcgen05.mma / tcgen05.commit
+//   warps 18-19 scouts: max|x| per cell of the next tile (per-frame power-of-two scale), L2 prefetch, edge frames
 // Pipelines are mbarrier based (2-deep stage ring); see DESIGN.md for the protocol.
 // Math, layouts and the per-thread arithmetic: fe_gemm_layout.h / fe_gemm.cuh.
 #include <cuda.h>
@@ -23,11 +23,18 @@
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kScoutWarp0 = 2;      // warps 2, 3
-constexpr int kProducerWarp0 = 4;   // warps 4..7
-constexpr int kEpilogueWarp0 = 8;   // warps 8..15
+// Warp roles.  The warp scheduler favours high warp ids, so the light, latency-critical roles (loader, MMA
+// issuer, scouts) sit at the top and the heavy ones below them.
+constexpr int kThreads = 640;
+constexpr int kEpilogueWarp0 = 0;   // warps 0..7  (TMEM lane quarter = warp & 3)
 constexpr int kNumEpilogueWarps = 8;
+constexpr int kProducerWarp0 = 8;   // warps 8..15: warps 8-11 produce the first half of a stage's K range, 12-15 the second
+constexpr int kNumProducerWarps = 8;
+constexpr int kLoaderWarp = 16, kMmaWarp = 17;
+constexpr int kScoutWarp0 = 18;     // warps 18, 19
+// All roles fit the 96 registers/thread the 640-thread CTA is launched with, so no setmaxnreg rebalancing is
+// done.  (Note for later: setmaxnreg.inc draws from the registers the CTA was LAUNCHED with, not from the SM's
+// free registers — a budget summing to more than 96 x 640 blocks forever.)
 constexpr int kTileM = FE_GEMM_TILE_M;
 constexpr int kSampBoxBytes = kTileM * 128;         // 128 rows x 32 floats
 constexpr int kSampStageBytes = 2 * kSampBoxBytes;  // forward + backward box
@@ -35,7 +42,7 @@ constexpr int kAStageBytes = 8 * 2 * kTileM * 16;   // 32 KB
 constexpr int kCellFloats = 512;                    // scout granularity: four coalesced 512-byte warp loads
 constexpr int kMaxCells = 48;
 constexpr int kSideSlots = 3;                       // edge frames per tile: t = 0 and up to two at the end (slots in use: 1 + n_frames - nb_map)
-constexpr uint32_t kSpinLimit = 1u << 24;
+constexpr uint32_t kSpinLimit = 1u << 21;  // x (<= ~2 us suspended per try) : a few seconds
 
 struct gemm_args {
   const float* wave;
@@ -47,6 +54,7 @@ struct gemm_args {
   int64_t row_base;
   int32_t rows, n_frames, n_filter, hop, nhalf, nstages, kpairs;
   int32_t tiles_per_row, n_tiles, top_db_group, nb_map;
+  int32_t fb_in_smem;  // filterbank weight table copied to shared memory (when it fits), else read through L1
 };
 
 // ---- shared memory carve-up (offsets from a 1024-byte aligned base) -------------------------------
@@ -54,14 +62,14 @@ struct smem_layout {
   int samp, a_stage, b_stage, energies, fb, ctl, mid, cells, side, side_max, unscale, p128, bars, tmem_slot, total;
 };
 
-__host__ __device__ inline smem_layout make_layout(int nhalf, int kpairs, int n_filter, int side_slots) {
+__host__ __device__ inline smem_layout make_layout(int nhalf, int kpairs, int n_filter, int side_slots, bool fb_in_smem) {
   smem_layout L;
   int off = 0;
   L.samp = off;      off += 2 * kSampStageBytes;                        // 64 KB, 1024-aligned boxes
   L.a_stage = off;   off += 2 * kAStageBytes;                           // 64 KB
   L.b_stage = off;   off += 2 * fe_gemm_b_stage_bytes(nhalf);           // 64 KB at nhalf = 128
   L.energies = off;  off += 2 * n_filter * kTileM * 4;                  // two column groups: 20 KB at 20 filters
-  L.fb = off;        off += nhalf * (int)sizeof(fe_gemm_fbw);
+  L.fb = off;        off += fb_in_smem ? nhalf * (int)sizeof(fe_gemm_fbw) : 0;
   L.ctl = off;       off += (int)sizeof(fe_gemm_fbctl);
   L.mid = off;       off += 2 * kpairs * 4;
   L.cells = off;     off += 2 * kMaxCells * 4;
@@ -71,7 +79,7 @@ __host__ __device__ inline smem_layout make_layout(int nhalf, int kpairs, int n_
   // last stage of tile i+1 only after the epilogue of tile i has read its copy, so one buffer suffices.
   const int pe_bufs = (kpairs / FE_GEMM_STAGE_J) >= 3 ? 1 : 2;
   L.unscale = off;   off += pe_bufs * kTileM * 4;
-  L.p128 = off;      off += pe_bufs * kTileM * 4;
+  L.p128 = off;      off += pe_bufs * 2 * kTileM * 8;                   // per producer half: (Re, Im) of bin n_fft/4
   off = (off + 15) & ~15;
   L.bars = off;      off += 16 * 8;
   L.tmem_slot = off; off += 16;
@@ -80,7 +88,7 @@ __host__ __device__ inline smem_layout make_layout(int nhalf, int kpairs, int n_
 }
 
 enum { BAR_SAMP_FULL = 0, BAR_STAGE_EMPTY = 2, BAR_A_FULL = 4, BAR_ACC_FULL = 6, BAR_ACC_EMPTY = 7,
-       BAR_SCOUT_FULL = 8, BAR_SCOUT_EMPTY = 10, BAR_COUNT = 12 };
+       BAR_SCOUT_FULL = 8, BAR_SCOUT_EMPTY = 10, BAR_SAMP_EMPTY = 12, BAR_B_FULL = 14, BAR_COUNT = 16 };
 
 #ifdef FE_GEMM_TRACE
 // debug build only: SM-clock timestamps of pipeline events of CTA 0 into the (enlarged) error-flag buffer
@@ -218,7 +226,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
     return;
   }
 
-  const smem_layout L = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map);
+  const smem_layout L = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map, a.fb_in_smem != 0);
   const int side_slots = 1 + a.n_frames - a.nb_map;
   const int pe_stride = a.nstages >= 3 ? 0 : kTileM;  // see make_layout
   const int side_floats = 2 * a.kpairs;  // per edge slot: forward[kpairs] + backward in box order [kpairs]
@@ -227,6 +235,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
 
   float* s_energy = reinterpret_cast<float*>(smem + L.energies);
+  const fe_gemm_fbw* g_fb = reinterpret_cast<const fe_gemm_fbw*>(blob + h->off_gemm_fb);
   fe_gemm_fbw* s_fb = reinterpret_cast<fe_gemm_fbw*>(smem + L.fb);
   fe_gemm_fbctl* s_ctl = reinterpret_cast<fe_gemm_fbctl*>(smem + L.ctl);
   float* s_mid = reinterpret_cast<float*>(smem + L.mid);
@@ -234,15 +243,14 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
   float* s_side = reinterpret_cast<float*>(smem + L.side);
   float* s_side_max = reinterpret_cast<float*>(smem + L.side_max);
   float* s_unscale = reinterpret_cast<float*>(smem + L.unscale);
-  float* s_p128 = reinterpret_cast<float*>(smem + L.p128);
+  float2* s_p128 = reinterpret_cast<float2*>(smem + L.p128);  // [buffer][half][frame]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const uint32_t bars = smem_u32(smem + L.bars);
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
 
   // ---- one-time setup -----------------------------------------------------------------------------
   {
-    const fe_gemm_fbw* gfb = reinterpret_cast<const fe_gemm_fbw*>(blob + h->off_gemm_fb);
-    for (int i = tid; i < a.nhalf; i += kThreads) s_fb[i] = gfb[i];
+    if (a.fb_in_smem) for (int i = tid; i < a.nhalf; i += kThreads) s_fb[i] = g_fb[i];
     const int32_t* gctl = reinterpret_cast<const int32_t*>(blob + h->off_gemm_fbflag);
     for (int i = tid; i < (int)(sizeof(fe_gemm_fbctl) / 4); i += kThreads) reinterpret_cast<int32_t*>(s_ctl)[i] = gctl[i];
     const float* gmid = reinterpret_cast<const float*>(blob + h->off_gemm_mid);
@@ -254,17 +262,21 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
     mbar_init(bar(BAR_SAMP_FULL + 1), 1);
     mbar_init(bar(BAR_STAGE_EMPTY + 0), 1);
     mbar_init(bar(BAR_STAGE_EMPTY + 1), 1);
-    mbar_init(bar(BAR_A_FULL + 0), 4);
-    mbar_init(bar(BAR_A_FULL + 1), 4);
+    mbar_init(bar(BAR_A_FULL + 0), kNumProducerWarps);
+    mbar_init(bar(BAR_A_FULL + 1), kNumProducerWarps);
     mbar_init(bar(BAR_ACC_FULL), 1);
     mbar_init(bar(BAR_ACC_EMPTY), kNumEpilogueWarps);
     mbar_init(bar(BAR_SCOUT_FULL + 0), 2);
     mbar_init(bar(BAR_SCOUT_FULL + 1), 2);
-    mbar_init(bar(BAR_SCOUT_EMPTY + 0), 4);
-    mbar_init(bar(BAR_SCOUT_EMPTY + 1), 4);
+    mbar_init(bar(BAR_SCOUT_EMPTY + 0), kNumProducerWarps);
+    mbar_init(bar(BAR_SCOUT_EMPTY + 1), kNumProducerWarps);
+    mbar_init(bar(BAR_SAMP_EMPTY + 0), kNumProducerWarps);
+    mbar_init(bar(BAR_SAMP_EMPTY + 1), kNumProducerWarps);
+    mbar_init(bar(BAR_B_FULL + 0), 1);
+    mbar_init(bar(BAR_B_FULL + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -275,7 +287,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
   const int T = (int)a.T;
   const int hop = a.hop;
 
-  if (warp == 0) {
+  if (warp == kLoaderWarp) {
     // ================================ loader ==========================================================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&wave_map) : "memory");
@@ -287,21 +299,25 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
         const int t0 = (tile - row_local * a.tiles_per_row) * kTileM;
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
-          mbar_wait(bar(BAR_STAGE_EMPTY + s), par ^ 1u, a.error_flag, 1);
+          // the sample boxes of slot s are free once the producers have read them (two stages ago) ...
+          mbar_wait(bar(BAR_SAMP_EMPTY + s), par ^ 1u, a.error_flag, 1);
           FE_TRACE(0, lit, q);
-          mbar_arrive_expect_tx(bar(BAR_SAMP_FULL + s), 2u * kSampBoxBytes + b_stage_bytes);
+          mbar_arrive_expect_tx(bar(BAR_SAMP_FULL + s), 2u * kSampBoxBytes);
           const uint32_t dst = smem_u32(smem + L.samp + s * kSampStageBytes);
           // forward box : block t0 + m,     columns 32q .. 32q+31        = x[c + 32q + e]
           // backward box: block t0 - 1 + m, columns hop-32q-32 .. hop-32q-1 = x[c - 32q - 32 + e]
           //               (16-byte aligned columns: an odd start column made the TMA fault)
           tma_box_3d(dst, &wave_map, bar(BAR_SAMP_FULL + s), 32 * q, t0, row_local);
           tma_box_3d(dst + kSampBoxBytes, &wave_map, bar(BAR_SAMP_FULL + s), hop - 32 * q - 32, t0 - 1, row_local);
+          // ... the DFT operand slot only when the MMAs that read it have retired
+          mbar_wait(bar(BAR_STAGE_EMPTY + s), par ^ 1u, a.error_flag, 9);
+          mbar_arrive_expect_tx(bar(BAR_B_FULL + s), b_stage_bytes);
           bulk_g2s(smem_u32(smem + L.b_stage + s * b_stage_bytes), gB + (size_t)q * b_stage_bytes, b_stage_bytes,
-                   bar(BAR_SAMP_FULL + s));
+                   bar(BAR_B_FULL + s));
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================================ MMA issuer ======================================================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(a.nhalf >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -315,7 +331,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
         FE_TRACE(7, it, 0);
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
-          mbar_wait(bar(BAR_SAMP_FULL + s), par, a.error_flag, 3);   // DFT operand stage landed
+          mbar_wait(bar(BAR_B_FULL + s), par, a.error_flag, 3);      // DFT operand stage landed
           mbar_wait(bar(BAR_A_FULL + s), par, a.error_flag, 4);      // producers wrote the A stage
           tc_fence_after();
           FE_TRACE(3, it, q);
@@ -337,8 +353,8 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
         }
       }
     }
-  } else if (warp < kProducerWarp0) {
-    // ================================ scouts (warps 2, 3) =============================================
+  } else if (warp >= kScoutWarp0) {
+    // ================================ scouts (warps 18, 19) =============================================
     // Per-tile max|x| over 128-float cells (one coalesced warp load each) for the per-frame fp16 scale,
     // one tile ahead of the producers; the reads also pull the tile's samples into L2 ahead of the TMA.
     // Warp 2 additionally gathers the reflect-padded samples of edge frames into side buffers.
@@ -417,9 +433,13 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
       if (sw == 0 && lane == 0) FE_TRACE(11, it, 0);
       if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL + pb));
     }
-  } else if (warp < kEpilogueWarp0) {
-    // ================================ producers (warps 4..7) ==========================================
-    const int m = (warp - kProducerWarp0) * 32 + lane;  // tile row = TMEM lane
+  } else if (warp >= kProducerWarp0) {
+    // ================================ producers (warps 8..15) =========================================
+    // warp pair (w, w+4) shares 32 frames: warps 4-7 produce sample pairs j = 32q .. 32q+15 of every stage
+    // (K chunk 0 of the A tiles), warps 8-11 j = 32q+16 .. 32q+31 (K chunk 1)
+    const int pw = warp - kProducerWarp0;
+    const int half = pw >> 2;
+    const int m = (pw & 3) * 32 + lane;  // tile row = TMEM lane
     const float* mid_re_w = s_mid;
     const float* mid_im_w = s_mid + a.kpairs;
     const int swz = m & 7;
@@ -453,34 +473,38 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
         if (warp == kProducerWarp0 && lane == 0) FE_TRACE(1, it, q);
         const unsigned char* fbox = slot < 0 ? smem + L.samp + s * kSampStageBytes + m * 128 : side_f + q * 128;
         const unsigned char* bbox = slot < 0 ? fbox + kSampBoxBytes : side_f + a.kpairs * 4 + q * 128;
-        unsigned char* a_row = smem + L.a_stage + s * kAStageBytes + m * 16;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          // forward elements 16*half .. +15 = x[c + j0 + i].  Backward: x[c - j0 - i] is box element
-          // 32 - 16*half - i; the 16 box elements 16*(1-half) .. +15 give i = 1..15 (reversed) and, in their
-          // first slot, the i = 0 sample of the NEXT half (carried over; the centre sample itself for j = 0).
-          float fwd[16], bwd[16], buf[16];
+        // forward elements 16*half .. +15 = x[c + j0 + i].  Backward: x[c - j0 - i] is box element
+        // 32 - 16*half - i: elements 16*(1-half) .. +15 give i = 1..15 (reversed); i = 0 is element 16 of the
+        // box (second half) or the first element of the previous stage's box / the centre sample (first half)
+        float fwd[16], bwd[16], buf[16];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const float4 f = *reinterpret_cast<const float4*>(fbox + (((4 * half + ch) ^ my_swz) << 4));
-            fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
-            const float4 b = *reinterpret_cast<const float4*>(bbox + (((4 * (1 - half) + ch) ^ my_swz) << 4));
-            buf[4 * ch + 0] = b.x; buf[4 * ch + 1] = b.y; buf[4 * ch + 2] = b.z; buf[4 * ch + 3] = b.w;
-          }
-          bwd[0] = (q == 0 && half == 0) ? fwd[0] : carry;
-#pragma unroll
-          for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
-          carry = buf[0];
-          fe_u4 chunk[8];
-          fe_gemm_produce_half(fwd, bwd, scale, 32 * q + 16 * half, mid_re_w, mid_im_w, mid_re, mid_im, chunk);
-#pragma unroll
-          for (int sf = 0; sf < 8; ++sf) {
-            *reinterpret_cast<fe_u4*>(a_row + sf * fe_gemm_tile_bytes(kTileM) + half * kTileM * 16) = chunk[sf];
-          }
+        for (int ch = 0; ch < 4; ++ch) {
+          const float4 f = *reinterpret_cast<const float4*>(fbox + (((4 * half + ch) ^ my_swz) << 4));
+          fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
+          const float4 bq = *reinterpret_cast<const float4*>(bbox + (((4 * (1 - half) + ch) ^ my_swz) << 4));
+          buf[4 * ch + 0] = bq.x; buf[4 * ch + 1] = bq.y; buf[4 * ch + 2] = bq.z; buf[4 * ch + 3] = bq.w;
         }
+        if (half == 0) {
+          bwd[0] = (q == 0) ? fwd[0] : carry;
+          carry = *reinterpret_cast<const float*>(bbox + ((0 ^ my_swz) << 4));   // element 0: x[c - 32(q+1)]
+        } else {
+          bwd[0] = *reinterpret_cast<const float*>(bbox + ((4 ^ my_swz) << 4));  // element 16
+        }
+#pragma unroll
+        for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
+        // samples are in registers: release the sample slot to the loader
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_SAMP_EMPTY + s));
+        fe_u4 chunk[8];
+        fe_gemm_produce_half(fwd, bwd, scale, 32 * q + 16 * half, mid_re_w, mid_im_w, mid_re, mid_im, chunk);
+        // the A slot is free once the MMAs of its previous use have retired
+        mbar_wait(bar(BAR_STAGE_EMPTY + s), par ^ 1u, a.error_flag, 10);
+        unsigned char* a_row = smem + L.a_stage + s * kAStageBytes + half * kTileM * 16 + m * 16;
+#pragma unroll
+        for (int sf = 0; sf < 8; ++sf) *reinterpret_cast<fe_u4*>(a_row + sf * fe_gemm_tile_bytes(kTileM)) = chunk[sf];
         if (q == a.nstages - 1) {
-          s_unscale[pb * pe_stride + m] = unscale * unscale;
-          s_p128[pb * pe_stride + m] = fmaf(mid_re, mid_re, mid_im * mid_im);
+          if (half == 0) s_unscale[pb * pe_stride + m] = unscale * unscale;
+          s_p128[(pb * pe_stride) * 2 + half * kTileM + m] = make_float2(mid_re, mid_im);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -493,7 +517,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
       }
     }
   } else {
-    // ================================ epilogue (warps 8..15) ==========================================
+    // ================================ epilogue (warps 0..7) =========================================
     const int ew = warp - kEpilogueWarp0;
     const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are the ones this warp may read
     const int grp = ew >> 2;               // column half
@@ -512,11 +536,14 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
       tc_fence_after();
       if (ew == 0 && lane == 0) FE_TRACE(4, it, 0);
       const float us2 = s_unscale[pb * pe_stride + m];
-      const float p_mid = s_p128[pb * pe_stride + m];
+      const float2 pm0 = s_p128[(pb * pe_stride) * 2 + m], pm1 = s_p128[(pb * pe_stride) * 2 + kTileM + m];
+      const float mid_r = pm0.x + pm1.x, mid_i = pm0.y + pm1.y;
+      const float p_mid = fmaf(mid_r, mid_r, mid_i * mid_i);
       // each column group sums into its own [filter][frame] array (the two groups meet on the filters
       // around their boundary); a thread only ever touches its own frame's column, so plain updates do
       float* ecol = s_energy + grp * nfil * kTileM + m;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const fe_gemm_fbw* fbw = a.fb_in_smem ? s_fb : g_fb;
       float alo[FE_GEMM_FB_SPAN], ahi[FE_GEMM_FB_SPAN];
 #pragma unroll 1
       for (int k0 = k_begin; k0 < k_end; k0 += 8) {
@@ -530,7 +557,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
           for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) alo[j] = ahi[j] = 0.0f;
         }
         tmem_ld_wait();
-        fe_gemm_epi_cols<8>(s_fb + k0, ce, co, se, so, alo, ahi);
+        fe_gemm_epi_cols<8>(fbw + k0, ce, co, se, so, alo, ahi);
         if ((k0 & (FE_GEMM_CHUNK - 1)) == FE_GEMM_CHUNK - 8) {
           // end of a 16-column chunk: add its 4 + 4 sums to the frame's filter sums
           const int c = k0 / FE_GEMM_CHUNK;
@@ -579,7 +606,7 @@ fe_gemm_kernel(const __grid_constant__ CUtensorMap wave_map, const gemm_args a) 
   // ---- teardown -------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
@@ -669,7 +696,8 @@ cudaError_t fe_gemm_launch(const b200fe_params* p, const fe_fft_args& fa, int64_
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
-  const smem_layout L = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map);
+  a.fb_in_smem = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map, true).total <= 227 * 1024;
+  const smem_layout L = make_layout(a.nhalf, a.kpairs, a.n_filter, 1 + a.n_frames - a.nb_map, a.fb_in_smem != 0);
   const int smem = L.total;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static int attr_done = 0;
