@@ -11,7 +11,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200fe.so")
+# B200FE_LIB: developer hook to load an instrumented build (e.g. the FE_GEMM_TRACE pipeline-timeline build)
+LIB_PATH = os.environ.get("B200FE_LIB") or os.path.join(_HERE, "lib", "libb200fe.so")
 
 ABI_VERSION = 1
 

@@ -252,7 +252,10 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
     if (energies_only) fa.out = out + (size_t)r0 * row_energy_floats;
     if (variant == B200FE_VARIANT_DFT_GEMM) {
       int launches = 0;
-      e = fe_gemm_launch(p, fa, r0, nr, gemm_ws, stream, &launches);
+      if (fe_stream_supported(p, T, nr) && !getenv("B200FE_LEGACY_GEMM"))
+        e = fe_stream_launch(p, fa, r0, nr, gemm_ws, stream, &launches);
+      else
+        e = fe_gemm_launch(p, fa, r0, nr, gemm_ws, stream, &launches);
       if (e != cudaSuccess) return cuda_fail(e, "dft-gemm kernel launch");
       g_launches += launches;
     } else {

@@ -46,7 +46,12 @@ struct fe_blob_header {
   int32_t off_gemm_fb;     // fe_gemm_fbw[gemm_nhalf] chunk-local filterbank weights (fe_gemm_layout.h)
   int32_t off_gemm_fbflag; // fe_gemm_fbctl
   int32_t off_gemm_mid;    // float[2][gemm_kpairs]  true-unit weights of bin n_fft/4 (Re from a_e, Im from a_o)
-  int32_t reserved[8];
+  // ---- streaming tcgen05 kernel (fe_stream.cu): sliding even/odd filter accumulators of the drain ----
+  int32_t stream_ok;       // 1 when the drain tables below are present (filterbank qualifies)
+  int32_t off_gemm_dw;     // fe_drain_w[gemm_nhalf + 1]   per GEMM column (+ bin n_fft/4): weights of the 4 accumulators
+  int32_t off_gemm_dctl;   // uint32[gemm_nhalf/8 + 1]     per 8-column batch: switch flags, bit 4*i + a
+  int32_t off_gemm_dids;   // fe_drain_ids[gemm_nhalf + 1] filter ids of the 4 accumulators after the column's switches
+  int32_t reserved[4];
 };
 
 static inline int64_t fe_align16(int64_t v) { return (v + 15) & ~(int64_t)15; }

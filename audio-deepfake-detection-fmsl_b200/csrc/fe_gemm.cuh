@@ -127,4 +127,97 @@ FE_HD void fe_gemm_epi_cols(const fe_gemm_fbw* w, const float* ce, const float* 
   }
 }
 
+// =====================================================================================================
+// Streaming kernel (fe_stream.cu)
+// =====================================================================================================
+
+// One production unit = 16 sample pairs j = j0 .. j0+15 of one frame, like fe_gemm_produce_half, but the
+// scale is folded into the fold:  bs = b*s ; a_e*s = fma(f, s, bs) ; a_o*s = fma(f, s, -bs)  (s is a power of
+// two, so both are exactly (f +- b)*s) and bin n_fft/4 is accumulated from the SCALED values.
+FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scale, const float* mid_re_w,
+                                  const float* mid_im_w, float& mid_re, float& mid_im, fe_u4* chunk) {
+  uint32_t hi[4][4], lo[4][4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int i0 = 4 * w;
+    float ae[4], ao[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float bs = bwd[i0 + u] * scale;
+      ae[u] = fmaf(fwd[i0 + u], scale, bs);
+      ao[u] = fmaf(fwd[i0 + u], scale, -bs);
+    }
+    mid_re = fmaf(ae[0], mid_re_w[i0], mid_re);
+    mid_re = fmaf(ae[2], mid_re_w[i0 + 2], mid_re);
+    mid_im = fmaf(ao[1], mid_im_w[i0 + 1], mid_im);
+    mid_im = fmaf(ao[3], mid_im_w[i0 + 3], mid_im);
+    float r0, r1;
+    hi[0][w] = fe_pack_hi(ae[0], ae[2], r0, r1); lo[0][w] = fe_pack_lo(r0, r1);
+    hi[1][w] = fe_pack_hi(ae[1], ae[3], r0, r1); lo[1][w] = fe_pack_lo(r0, r1);
+    hi[2][w] = fe_pack_hi(ao[0], ao[2], r0, r1); lo[2][w] = fe_pack_lo(r0, r1);
+    hi[3][w] = fe_pack_hi(ao[1], ao[3], r0, r1); lo[3][w] = fe_pack_lo(r0, r1);
+  }
+#pragma unroll
+  for (int sub = 0; sub < 4; ++sub) {
+    chunk[sub * 2 + 0] = fe_u4{hi[sub][0], hi[sub][1], hi[sub][2], hi[sub][3]};
+    chunk[sub * 2 + 1] = fe_u4{lo[sub][0], lo[sub][1], lo[sub][2], lo[sub][3]};
+  }
+}
+
+// ---- drain: sliding even/odd filter accumulators (tables: fe_gemm_layout.h) ------------------------------
+struct fe_drain_state {
+  float acc[4];
+  int id[4];
+};
+
+// adds one finished accumulator to the frame's filter sum (e_col = this frame's column of the [filter][128] array)
+FE_HD void fe_drain_emit(float* e_col, int nfil, int id, float v, float us2) {
+  if (id >= 0 && id < nfil) e_col[id * FE_GEMM_TILE_M] = fmaf(v, us2, e_col[id * FE_GEMM_TILE_M]);
+}
+
+// the (rare, thread-uniform) switches of one column
+FE_HD void fe_drain_switch(unsigned flags, fe_drain_ids ids, fe_drain_state& st, float* e_col, int nfil, float us2) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (flags & (1u << a)) {
+      fe_drain_emit(e_col, nfil, st.id[a], st.acc[a], us2);
+      st.acc[a] = 0.0f;
+      st.id[a] = ids.id[a];
+    }
+  }
+}
+
+// NB consecutive columns starting at a multiple of 8 (ctl = the batch's switch word, w / ids at the first column)
+template <int NB>
+FE_HD void fe_drain_cols(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, const float* ce, const float* co,
+                         const float* se, const float* so, fe_drain_state& st, float* e_col, int nfil, float us2) {
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const float re1 = ce[i] + co[i], im1 = se[i] + so[i], re2 = ce[i] - co[i], im2 = so[i] - se[i];
+    const float p1 = fmaf(re1, re1, im1 * im1);  // |X[k]|^2 (scaled units)
+    const float p2 = fmaf(re2, re2, im2 * im2);  // |X[n_fft/2 - k]|^2
+    const unsigned fl = (ctl >> (4 * i)) & 15u;
+    if (fl) fe_drain_switch(fl, ids[i], st, e_col, nfil, us2);
+    const fe_drain_w t = w[i];
+    st.acc[0] = fmaf(p1, t.w[0], st.acc[0]);
+    st.acc[1] = fmaf(p1, t.w[1], st.acc[1]);
+    st.acc[2] = fmaf(p2, t.w[2], st.acc[2]);
+    st.acc[3] = fmaf(p2, t.w[3], st.acc[3]);
+  }
+}
+
+// bin n_fft/4 (column index nhalf of the tables): only the lo-run accumulators
+FE_HD void fe_drain_mid(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, float p_mid, fe_drain_state& st,
+                        float* e_col, int nfil, float us2) {
+  const unsigned fl = ctl & 3u;
+  if (fl) fe_drain_switch(fl, ids[0], st, e_col, nfil, us2);
+  st.acc[0] = fmaf(p_mid, w[0].w[0], st.acc[0]);
+  st.acc[1] = fmaf(p_mid, w[0].w[1], st.acc[1]);
+}
+
+FE_HD void fe_drain_flush(fe_drain_state& st, float* e_col, int nfil, float us2) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a) fe_drain_emit(e_col, nfil, st.id[a], st.acc[a], us2);
+}
+
 #endif  // FE_GEMM_CUH_

@@ -13,4 +13,8 @@ int64_t fe_gemm_workspace_bytes(const b200fe_params* p, int64_t chunk_rows, int6
 // fe_launch_fft(mode 1).
 cudaError_t fe_gemm_launch(const b200fe_params* p, const fe_fft_args& fa, int64_t row_base, int64_t rows,
                            void* gemm_ws, cudaStream_t stream, int* launches);
+// Streaming kernel (fe_stream.cu): same contract as fe_gemm_launch; needs tables with stream_ok.
+bool fe_stream_supported(const b200fe_params* p, int64_t T, int64_t rows);
+cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int64_t row_base, int64_t rows,
+                             void* gemm_ws, cudaStream_t stream, int* launches);
 #endif

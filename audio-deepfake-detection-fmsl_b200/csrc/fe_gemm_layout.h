@@ -41,6 +41,21 @@ struct fe_gemm_fbctl {
   int32_t pad[3];
 };
 
+// ---- drain tables of the streaming kernel (fe_stream.cu) ------------------------------------------------
+// A drain thread owns one frame and a range of GEMM columns (nhalf/4 consecutive columns per warp, "column
+// group").  Column k carries bin k (the ascending "lo" run) and bin n_fft/2 - k (the descending "hi" run).
+// Every bin may have at most one even-indexed and one odd-indexed filter with non-zero weight (true for
+// triangular banks), so each run needs two accumulators: accumulator a = 2*run + parity.  Walking the columns,
+// an accumulator is emitted (added to the frame's filter sum) and re-targeted whenever the filter of its parity
+// changes ("switch"); switches are the same for all threads, so they are table driven and branch-uniform.
+struct alignas(16) fe_drain_w {
+  float w[4];        // weights of bin k for (lo even, lo odd) and of bin n_fft/2 - k for (hi even, hi odd)
+};
+struct fe_drain_ids {
+  int8_t id[4];      // filter of each accumulator once this column's switches are done (-1: none yet)
+};
+#define FE_DRAIN_GROUPS 4   // column groups (warps per TMEM lane quarter)
+
 // UMMA K-major, no-swizzle operand tile of `rows` rows x 16 K-values (one K=16 MMA step):
 // [K chunk of 8][row][8 halfs] -> descriptor LBO (K-chunk stride) = rows*16 B, SBO (8-row group) = 128 B.
 FE_HD int fe_gemm_operand_offset(int rows, int r, int kk) { return (kk >> 3) * rows * 16 + r * 16 + (kk & 7) * 2; }

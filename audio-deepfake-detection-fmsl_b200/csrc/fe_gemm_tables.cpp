@@ -53,8 +53,66 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
   off = fe_align16(off + (int64_t)sizeof(fe_gemm_fbctl));
   h->off_gemm_mid = (int32_t)off;
   off = fe_align16(off + (int64_t)2 * g.kpairs * 4);
+  h->off_gemm_dw = (int32_t)off;
+  off = fe_align16(off + (int64_t)(g.nhalf + 1) * sizeof(fe_drain_w));
+  h->off_gemm_dctl = (int32_t)off;
+  off = fe_align16(off + (int64_t)(g.nhalf / 8 + 1) * 4);
+  h->off_gemm_dids = (int32_t)off;
+  off = fe_align16(off + (int64_t)(g.nhalf + 1) * sizeof(fe_drain_ids));
   h->gemm_ok = 1;  // provisional: fe_gemm_pack clears it when the window / filterbank do not qualify
+  h->stream_ok = 0;
   return off;
+}
+
+// Drain tables of the streaming kernel (fe_gemm_layout.h): per column the weights of the four sliding
+// accumulators, the switch flags and the filter ids after the switches.  Returns false when the filterbank
+// does not qualify (a bin with two filters of the same parity, or a filter shared by non-adjacent groups).
+static bool pack_drain_tables(const fe_blob_header* h, const float* fbank, int nfil, int nhalf, char* base) {
+  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nfil > FE_GEMM_MAX_FILTERS) return false;
+  fe_drain_w* dw = (fe_drain_w*)(base + h->off_gemm_dw);
+  uint32_t* dctl = (uint32_t*)(base + h->off_gemm_dctl);
+  fe_drain_ids* dids = (fe_drain_ids*)(base + h->off_gemm_dids);
+  memset(dw, 0, (size_t)(nhalf + 1) * sizeof(fe_drain_w));
+  memset(dctl, 0, (size_t)(nhalf / 8 + 1) * 4);
+  const int nyq = 2 * nhalf, cpg = nhalf / FE_DRAIN_GROUPS;
+  std::vector<unsigned> touched(nfil, 0u);
+  // filter of parity `par` with weight on `bin` (-1: none, -2: more than one)
+  auto filter_of = [&](int bin, int par) {
+    int f_found = -1;
+    for (int f = par; f < nfil; f += 2)
+      if (fbank[(int64_t)bin * nfil + f] != 0.0f) { if (f_found >= 0) return -2; f_found = f; }
+    return f_found;
+  };
+  for (int g = 0; g < FE_DRAIN_GROUPS; ++g) {
+    int cur[4] = {-1, -1, -1, -1};
+    const int k_end = (g + 1) * cpg + (g == FE_DRAIN_GROUPS - 1 ? 1 : 0);  // the last group also takes bin n_fft/4
+    for (int k = g * cpg; k < k_end; ++k) {
+      unsigned flags = 0;
+      for (int run = 0; run < 2; ++run) {
+        if (k == nhalf && run == 1) continue;
+        const int bin = run == 0 ? k : nyq - k;
+        for (int par = 0; par < 2; ++par) {
+          const int a = 2 * run + par;
+          const int f = filter_of(bin, par);
+          if (f == -2) return false;
+          if (f < 0) continue;
+          dw[k].w[a] = fbank[(int64_t)bin * nfil + f];
+          touched[f] |= 1u << g;
+          if (f != cur[a]) { flags |= 1u << a; cur[a] = f; }
+        }
+      }
+      for (int a = 0; a < 4; ++a) dids[k].id[a] = (int8_t)cur[a];
+      dctl[k / 8] |= flags << (4 * (k % 8));
+    }
+  }
+  // the two emission buffers are indexed by group parity: a filter may only be shared by adjacent groups
+  for (int f = 0; f < nfil; ++f) {
+    const unsigned m = touched[f];
+    if (m == 0) continue;
+    const unsigned low = m & (0u - m);
+    if (m != low && m != (low | (low << 1))) return false;
+  }
+  return true;
 }
 
 int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* window, const float* fbank,
@@ -111,6 +169,7 @@ int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* win
     for (int j = 0; j < FE_GEMM_FB_SPAN; ++j)
       ctl->mid_w[j] = (f1 >= 0 && f0 + j < nfil) ? fbank[(int64_t)g.nhalf * nfil + f0 + j] : 0.0f;
   }
+  h->stream_ok = pack_drain_tables(h, fbank, nfil, g.nhalf, base) ? 1 : 0;
   // ---- bin n_fft/4 (handled on the CUDA cores): true-unit weights ------------------------------
   float* mid = (float*)(base + h->off_gemm_mid);
   for (int j = 0; j < g.kpairs; ++j) {

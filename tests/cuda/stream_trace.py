@@ -1,0 +1,27 @@
+"""FE_GEMM_TRACE build only (make LIBDIR=../lib_trace EXTRA_NVFLAGS=-DFE_GEMM_TRACE; B200FE_LIB=...): SM-clock
+timeline of CTA 0 of the streaming kernel."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import numpy as np, torch
+import b200_frontend as fe
+import helpers
+m = fe.LFCCDelta(**helpers.LFCC_CFG, variant="dft_gemm")
+eng = m.engine
+R = 1184
+x = (0.1 * torch.randn(R, 64600, device="cuda")).clamp_(-1, 1)
+for _ in range(2):
+    e = eng.fbank_energies(x)
+torch.cuda.synchronize()
+ws = eng._workspace[x.device]
+nbytes = eng.lib.b200fe_workspace_bytes(C.byref(eng.params), R, 64600)
+tail = ws[nbytes - 65536: nbytes].cpu().numpy()
+print("flag", tail[:4].view(np.int32)[0])
+tr = np.frombuffer(tail[256:256 + 8 * 8 * 16 * 8].tobytes(), dtype=np.int64).reshape(8, 8, 16)
+base = tr[0, 0, 0]
+for it in range(7):
+    r = lambda q, e: int(tr[it, q, e] - base)
+    print("tile", it, "loader_start", r(0, 0), "samp_full", r(0, 1), "acc_full", r(0, 4), "drain_done", r(0, 5), "fin_done", r(0, 6),
+          "scout_done", r(0, 7), "zero_done", r(0, 8))
+    print("    produced(q):", [r(q, 2) for q in range(5)], " mma_issue(q):", [r(q, 3) for q in range(5)])
