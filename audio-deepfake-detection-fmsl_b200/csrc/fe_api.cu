@@ -180,8 +180,8 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
       fe_set_error("variant dft_gemm does not support this configuration / ragged input");
       return B200FE_ERR_UNSUPPORTED;
     }
-    if ((T & 3) != 0 || ((uintptr_t)wave & 15) != 0) {
-      fe_set_error("variant dft_gemm needs T %% 4 == 0 and a 16-byte aligned waveform (TMA)");
+    if (!fe_stream_supported(p, T, R) || ((uintptr_t)wave & 15) != 0) {
+      fe_set_error("variant dft_gemm needs T %% 4 == 0, T > n_fft/2 and a 16-byte aligned waveform (TMA)");
       return B200FE_ERR_UNSUPPORTED;
     }
     variant = B200FE_VARIANT_DFT_GEMM;
@@ -252,10 +252,7 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
     if (energies_only) fa.out = out + (size_t)r0 * row_energy_floats;
     if (variant == B200FE_VARIANT_DFT_GEMM) {
       int launches = 0;
-      if (fe_stream_supported(p, T, nr) && !getenv("B200FE_LEGACY_GEMM"))
-        e = fe_stream_launch(p, fa, r0, nr, gemm_ws, stream, &launches);
-      else
-        e = fe_gemm_launch(p, fa, r0, nr, gemm_ws, stream, &launches);
+      e = fe_stream_launch(p, fa, r0, nr, gemm_ws, stream, &launches);
       if (e != cudaSuccess) return cuda_fail(e, "dft-gemm kernel launch");
       g_launches += launches;
     } else {

@@ -41,17 +41,15 @@ struct fe_blob_header {
   int32_t gemm_ok;         // 1 when the tiles below are present
   int32_t gemm_kpairs;     // folded K rows per parity class (multiple of 16)
   int32_t gemm_nhalf;      // n_fft/4 : GEMM N (bins 0 .. n_fft/4-1; bin n_fft/4 handled apart)
-  int32_t off_gemm_b;      // __half operand tiles, see fe_gemm.cuh
+  int32_t off_gemm_b;      // __half operand tiles, see fe_gemm_layout.h
   int32_t gemm_b_bytes;
-  int32_t off_gemm_fb;     // fe_gemm_fbw[gemm_nhalf] chunk-local filterbank weights (fe_gemm_layout.h)
-  int32_t off_gemm_fbflag; // fe_gemm_fbctl
   int32_t off_gemm_mid;    // float[2][gemm_kpairs]  true-unit weights of bin n_fft/4 (Re from a_e, Im from a_o)
-  // ---- streaming tcgen05 kernel (fe_stream.cu): sliding even/odd filter accumulators of the drain ----
-  int32_t stream_ok;       // 1 when the drain tables below are present (filterbank qualifies)
+  // sliding even/odd filter accumulators of the drain (fe_gemm_layout.h)
   int32_t off_gemm_dw;     // fe_drain_w[gemm_nhalf + 1]   per GEMM column (+ bin n_fft/4): weights of the 4 accumulators
   int32_t off_gemm_dctl;   // uint32[gemm_nhalf/8 + 1]     per 8-column batch: switch flags, bit 4*i + a
   int32_t off_gemm_dids;   // fe_drain_ids[gemm_nhalf + 1] filter ids of the 4 accumulators after the column's switches
-  int32_t reserved[4];
+  int32_t gemm_nbuf;       // emission buffers of the drain: 2 (indexed by column-group parity) or 4 (one per group)
+  int32_t reserved[6];
 };
 
 static inline int64_t fe_align16(int64_t v) { return (v + 15) & ~(int64_t)15; }

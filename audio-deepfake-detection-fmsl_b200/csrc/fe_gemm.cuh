@@ -1,5 +1,5 @@
 // Per-thread arithmetic of the DFT-GEMM variant (see fe_gemm_layout.h for the math and layouts).
-// Everything here compiles for the device (used by fe_gemm.cu) and as plain C++ (tests/emu), so the
+// Everything here compiles for the device (used by fe_stream.cu) and as plain C++ (tests/emu), so the
 // fold / scale / fp16-split / filterbank-sweep logic is exercised on the CPU with the MMA replaced by
 // loops over the very same operand images.
 #ifndef FE_GEMM_CUH_
@@ -72,70 +72,38 @@ FE_HD void fe_gemm_frame_scale(float bound, float& scale, float& unscale) {
   unscale = fe_u2f((uint32_t)(-s - FE_GEMM_B_SCALE_LOG2 + 127) << 23);
 }
 
-// One half stage (16 sample pairs j = j0 .. j0+15, j0 a multiple of 16) of one frame:
-//   fwd[i] = x[c + j0 + i]        bwd[i] = x[c - j0 - i]          i = 0 .. 15
-// Produces the eight 16-byte K chunks (one per sub-GEMM x flavour) of the frame's A rows and updates
-// the directly evaluated bin n_fft/4 (true units).
-//   chunk[(sub*2 + flav)], sub: 0 = ce (a_e, even j), 1 = co (a_e, odd j), 2 = se (a_o, even j), 3 = so (a_o, odd j)
-FE_HD void fe_gemm_produce_half(const float* fwd, const float* bwd, float scale, int j0, const float* mid_re_w,
-                                const float* mid_im_w, float& mid_re, float& mid_im, fe_u4* chunk) {
-  uint32_t hi[4][4], lo[4][4];  // [sub][word]: 8 halfs = 4 words per chunk
-#pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    // word w of the even-j chunk holds j = j0 + 4w, j0 + 4w + 2 ; of the odd-j chunk j0 + 4w + 1, + 3
-    const int i0 = 4 * w;
-    const float ae0 = fwd[i0] + bwd[i0], ao0 = fwd[i0] - bwd[i0];
-    const float ae1 = fwd[i0 + 1] + bwd[i0 + 1], ao1 = fwd[i0 + 1] - bwd[i0 + 1];
-    const float ae2 = fwd[i0 + 2] + bwd[i0 + 2], ao2 = fwd[i0 + 2] - bwd[i0 + 2];
-    const float ae3 = fwd[i0 + 3] + bwd[i0 + 3], ao3 = fwd[i0 + 3] - bwd[i0 + 3];
-    mid_re = fmaf(ae0, mid_re_w[j0 + i0], mid_re);
-    mid_re = fmaf(ae2, mid_re_w[j0 + i0 + 2], mid_re);
-    mid_im = fmaf(ao1, mid_im_w[j0 + i0 + 1], mid_im);
-    mid_im = fmaf(ao3, mid_im_w[j0 + i0 + 3], mid_im);
-    float r0, r1;
-    hi[0][w] = fe_pack_hi(ae0 * scale, ae2 * scale, r0, r1); lo[0][w] = fe_pack_lo(r0, r1);
-    hi[1][w] = fe_pack_hi(ae1 * scale, ae3 * scale, r0, r1); lo[1][w] = fe_pack_lo(r0, r1);
-    hi[2][w] = fe_pack_hi(ao0 * scale, ao2 * scale, r0, r1); lo[2][w] = fe_pack_lo(r0, r1);
-    hi[3][w] = fe_pack_hi(ao1 * scale, ao3 * scale, r0, r1); lo[3][w] = fe_pack_lo(r0, r1);
-  }
-#pragma unroll
-  for (int sub = 0; sub < 4; ++sub) {
-    chunk[sub * 2 + 0] = fe_u4{hi[sub][0], hi[sub][1], hi[sub][2], hi[sub][3]};
-    chunk[sub * 2 + 1] = fe_u4{lo[sub][0], lo[sub][1], lo[sub][2], lo[sub][3]};
-  }
-}
-
-// ---- epilogue: NB consecutive GEMM columns of one 16-column chunk.  Powers of bins k and n_fft/2 - k
-// from the four accumulators (ce+co, se+so | ce-co, so-se), then 4 chunk-local filter sums per bin run
-// with dense weights (fe_gemm_layout.h): 8 flops + 8 FMAs per column, no data-dependent control flow.
-// The caller zeroes acc_lo / acc_hi at the start of a chunk and adds them to the frame's filter sums at
-// its end; the body is kept small (NB = 8) so the loop stays resident in the instruction cache.
-template <int NB>
-FE_HD void fe_gemm_epi_cols(const fe_gemm_fbw* w, const float* ce, const float* co, const float* se,
-                            const float* so, float* acc_lo, float* acc_hi) {
-#pragma unroll
-  for (int i = 0; i < NB; ++i) {
-    const float re1 = ce[i] + co[i], im1 = se[i] + so[i], re2 = ce[i] - co[i], im2 = so[i] - se[i];
-    const float p1 = fmaf(re1, re1, im1 * im1);  // |X[k]|^2           (scaled units)
-    const float p2 = fmaf(re2, re2, im2 * im2);  // |X[n_fft/2 - k]|^2
-    const fe_gemm_fbw t = w[i];
-#pragma unroll
-    for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) {
-      acc_lo[j] = fmaf(p1, t.lo[j], acc_lo[j]);
-      acc_hi[j] = fmaf(p2, t.hi[j], acc_hi[j]);
-    }
-  }
-}
-
 // =====================================================================================================
 // Streaming kernel (fe_stream.cu)
 // =====================================================================================================
 
-// One production unit = 16 sample pairs j = j0 .. j0+15 of one frame, like fe_gemm_produce_half, but the
+// Tile geometry of the frame stream.  The launch's rows are one stream of frames g = row * nF + t; a tile takes
+// `tile_frames` consecutive stream frames.  Hop block v of a row (samples [(v-1) hop, v hop); v = 0 and v = nF are
+// the reflect-padded edges) has stream index row (nF+1) + v; frame (row, t) reads blocks t (backward half) and
+// t + 1 (forward half), so a tile needs the nv consecutive stream blocks sv0 .. sv0 + nv - 1.
+struct fe_tile_geo {
+  int g0, count, row0, row_last, sv0, nv;
+};
+FE_HD fe_tile_geo fe_tile_geometry(int tile, int tile_frames, int total_frames, int nF) {
+  fe_tile_geo t;
+  t.g0 = tile * tile_frames;
+  t.count = total_frames - t.g0 < tile_frames ? total_frames - t.g0 : tile_frames;
+  t.row0 = t.g0 / nF;
+  const int g_last = t.g0 + t.count - 1;
+  t.row_last = g_last / nF;
+  t.sv0 = t.g0 + t.row0;
+  t.nv = t.count + (t.row_last - t.row0) + 1;
+  return t;
+}
+// frames per tile: 128 (the TMEM lanes) unless the utterances are so short that 128 frames would span more than
+// three of them (the sample buffer holds 132 hop blocks)
+FE_HD int fe_tile_frames(int nF) { return 2 * nF < FE_GEMM_TILE_M ? 2 * nF : FE_GEMM_TILE_M; }
+
+// One production unit = 16 sample pairs j = j0 .. j0+15 of one frame.  The
 // scale is folded into the fold:  bs = b*s ; a_e*s = fma(f, s, bs) ; a_o*s = fma(f, s, -bs)  (s is a power of
-// two, so both are exactly (f +- b)*s) and bin n_fft/4 is accumulated from the SCALED values.
-FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scale, const float* mid_re_w,
-                                  const float* mid_im_w, float& mid_re, float& mid_im, fe_u4* chunk) {
+// two, so both are exactly (f +- b)*s) and bin n_fft/4 is accumulated from the SCALED values with the
+// interleaved weight table midc[j] = (j even ? Re weight : Im weight) (four 16-byte broadcast loads per unit).
+FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scale, const float* midc,
+                                  float& mid_re, float& mid_im, fe_u4* chunk) {
   uint32_t hi[4][4], lo[4][4];
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
@@ -147,10 +115,11 @@ FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scal
       ae[u] = fmaf(fwd[i0 + u], scale, bs);
       ao[u] = fmaf(fwd[i0 + u], scale, -bs);
     }
-    mid_re = fmaf(ae[0], mid_re_w[i0], mid_re);
-    mid_re = fmaf(ae[2], mid_re_w[i0 + 2], mid_re);
-    mid_im = fmaf(ao[1], mid_im_w[i0 + 1], mid_im);
-    mid_im = fmaf(ao[3], mid_im_w[i0 + 3], mid_im);
+    const float m0 = midc[i0], m1 = midc[i0 + 1], m2 = midc[i0 + 2], m3 = midc[i0 + 3];
+    mid_re = fmaf(ae[0], m0, mid_re);
+    mid_im = fmaf(ao[1], m1, mid_im);
+    mid_re = fmaf(ae[2], m2, mid_re);
+    mid_im = fmaf(ao[3], m3, mid_im);
     float r0, r1;
     hi[0][w] = fe_pack_hi(ae[0], ae[2], r0, r1); lo[0][w] = fe_pack_lo(r0, r1);
     hi[1][w] = fe_pack_hi(ae[1], ae[3], r0, r1); lo[1][w] = fe_pack_lo(r0, r1);

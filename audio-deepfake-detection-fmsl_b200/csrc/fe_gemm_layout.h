@@ -1,4 +1,4 @@
-// Data layout shared by the host packer (fe_gemm_tables.cpp), the tcgen05 kernel (fe_gemm.cu) and
+// Data layout shared by the host packer (fe_gemm_tables.cpp), the tcgen05 kernel (fe_stream.cu) and
 // the CPU emulation (tests/emu) of the DFT-GEMM variant.
 //
 // Math.  A frame is win = 2*hop samples centred on c (torch.stft center=True); with the symmetric
@@ -22,26 +22,7 @@
 #define FE_GEMM_A_SCALE_LOG2 13   // per frame: 2*max|x| is scaled into [2^13, 2^14)
 #define FE_GEMM_STAGE_J 32        // sample pairs per pipeline stage: one K=16 MMA step per sub-GEMM
 
-// Filterbank tables of the epilogue.  GEMM column k carries bins k ("lo") and n_fft/2 - k ("hi").  Within
-// a chunk of 16 consecutive columns each of the two bin runs may only touch FE_GEMM_FB_SPAN consecutive
-// filters (true for triangular banks whose filters are at least 8 bins apart; checked by the packer), so a
-// thread accumulates each run into 4 chunk-local sums with dense weights — straight-line code, no
-// data-dependent control flow — and adds them to the per-frame filter sums once per chunk.
-#define FE_GEMM_FB_SPAN 4
-#define FE_GEMM_CHUNK 16
-struct alignas(16) fe_gemm_fbw {
-  float lo[FE_GEMM_FB_SPAN];  // weights of bin k for filters base_lo[chunk] + 0..3
-  float hi[FE_GEMM_FB_SPAN];  // weights of bin n_fft/2 - k for filters base_hi[chunk] + 0..3
-};
-// control block: first filter of each chunk's runs, and bin n_fft/4 (evaluated apart) as up to 4 filters
-struct fe_gemm_fbctl {
-  int32_t base_lo[16], base_hi[16];   // per chunk (nhalf / 16 <= 8 used)
-  int32_t mid_base;
-  float mid_w[FE_GEMM_FB_SPAN];
-  int32_t pad[3];
-};
-
-// ---- drain tables of the streaming kernel (fe_stream.cu) ------------------------------------------------
+// ---- drain tables ----------------------------------------------------------------------------------------
 // A drain thread owns one frame and a range of GEMM columns (nhalf/4 consecutive columns per warp, "column
 // group").  Column k carries bin k (the ascending "lo" run) and bin n_fft/2 - k (the descending "hi" run).
 // Every bin may have at most one even-indexed and one odd-indexed filter with non-zero weight (true for

@@ -26,7 +26,7 @@ gemm_geom geometry(const b200fe_params* p) {
   const int kpairs = p->win_length / 2;
   const int nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return g;
-  if (nhalf % 16 != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM
+  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM
   if (p->preemph != 0.0f) return g;
   g.ok = true;
   g.kpairs = kpairs;
@@ -47,10 +47,6 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
   h->off_gemm_b = (int32_t)off;
   h->gemm_b_bytes = g.nstages * fe_gemm_b_stage_bytes(g.nhalf);
   off = fe_align16(off + h->gemm_b_bytes);
-  h->off_gemm_fb = (int32_t)off;
-  off = fe_align16(off + (int64_t)g.nhalf * sizeof(fe_gemm_fbw));
-  h->off_gemm_fbflag = (int32_t)off;
-  off = fe_align16(off + (int64_t)sizeof(fe_gemm_fbctl));
   h->off_gemm_mid = (int32_t)off;
   off = fe_align16(off + (int64_t)2 * g.kpairs * 4);
   h->off_gemm_dw = (int32_t)off;
@@ -60,14 +56,13 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
   h->off_gemm_dids = (int32_t)off;
   off = fe_align16(off + (int64_t)(g.nhalf + 1) * sizeof(fe_drain_ids));
   h->gemm_ok = 1;  // provisional: fe_gemm_pack clears it when the window / filterbank do not qualify
-  h->stream_ok = 0;
   return off;
 }
 
-// Drain tables of the streaming kernel (fe_gemm_layout.h): per column the weights of the four sliding
+// Drain tables (fe_gemm_layout.h): per column the weights of the four sliding
 // accumulators, the switch flags and the filter ids after the switches.  Returns false when the filterbank
 // does not qualify (a bin with two filters of the same parity, or a filter shared by non-adjacent groups).
-static bool pack_drain_tables(const fe_blob_header* h, const float* fbank, int nfil, int nhalf, char* base) {
+static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, int nhalf, char* base) {
   if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nfil > FE_GEMM_MAX_FILTERS) return false;
   fe_drain_w* dw = (fe_drain_w*)(base + h->off_gemm_dw);
   uint32_t* dctl = (uint32_t*)(base + h->off_gemm_dctl);
@@ -105,21 +100,25 @@ static bool pack_drain_tables(const fe_blob_header* h, const float* fbank, int n
       dctl[k / 8] |= flags << (4 * (k % 8));
     }
   }
-  // the two emission buffers are indexed by group parity: a filter may only be shared by adjacent groups
+  // Column groups that share a filter must emit into different buffers.  Two buffers indexed by group parity do
+  // when a filter is only ever shared by adjacent groups; otherwise every group gets its own buffer (if the
+  // n_filter x 128 arrays still fit the 32 KB they alias).
+  bool adjacent_only = true;
   for (int f = 0; f < nfil; ++f) {
     const unsigned m = touched[f];
     if (m == 0) continue;
     const unsigned low = m & (0u - m);
-    if (m != low && m != (low | (low << 1))) return false;
+    if (m != low && m != (low | (low << 1))) adjacent_only = false;
   }
-  return true;
+  h->gemm_nbuf = adjacent_only ? 2 : FE_DRAIN_GROUPS;
+  return h->gemm_nbuf * nfil * FE_GEMM_TILE_M * 4 <= 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M);
 }
 
 int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* window, const float* fbank,
                      char* base) {
   if (!h->gemm_ok) return B200FE_OK;
   const gemm_geom g = geometry(p);
-  const int n_fft = p->n_fft, n_freq = n_fft / 2 + 1, nfil = p->n_filter;
+  const int n_fft = p->n_fft, nfil = p->n_filter;
   // ---- symmetric window about the frame centre -------------------------------------------------
   // centred window index i = j + win/2 for offset j from the centre; j = -win/2 is the lone sample
   std::vector<double> wj(g.kpairs);
@@ -133,43 +132,8 @@ int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* win
     if (fabs(a - b) > 1e-6 * wmax) { h->gemm_ok = 0; return B200FE_OK; }
     wj[j] = 0.5 * (a + b);
   }
-  // ---- filterbank: per 16-column chunk, each bin run touches at most 4 consecutive filters ----------
-  fe_gemm_fbw* fbw = (fe_gemm_fbw*)(base + h->off_gemm_fb);
-  fe_gemm_fbctl* ctl = (fe_gemm_fbctl*)(base + h->off_gemm_fbflag);
-  memset(ctl, 0, sizeof(*ctl));
-  const int nyq = n_fft / 2;
-  auto span_of = [&](int b_first, int b_last, int* lo_f, int* hi_f) {  // filters with weight on bins b_first..b_last
-    *lo_f = nfil; *hi_f = -1;
-    for (int b = b_first; b <= b_last; ++b)
-      for (int f = 0; f < nfil; ++f)
-        if (fbank[(int64_t)b * nfil + f] != 0.0f) { if (f < *lo_f) *lo_f = f; if (f > *hi_f) *hi_f = f; }
-  };
-  for (int c = 0; c < g.nhalf / FE_GEMM_CHUNK; ++c) {
-    const int k0 = c * FE_GEMM_CHUNK, k1 = k0 + FE_GEMM_CHUNK - 1;
-    int f0, f1;
-    span_of(k0, k1, &f0, &f1);
-    if (f1 >= 0 && f1 - f0 >= FE_GEMM_FB_SPAN) { h->gemm_ok = 0; return B200FE_OK; }
-    const int bl = f1 < 0 ? 0 : f0;
-    span_of(nyq - k1, nyq - k0, &f0, &f1);
-    if (f1 >= 0 && f1 - f0 >= FE_GEMM_FB_SPAN) { h->gemm_ok = 0; return B200FE_OK; }
-    const int bh = f1 < 0 ? 0 : f0;
-    ctl->base_lo[c] = bl;
-    ctl->base_hi[c] = bh;
-    for (int k = k0; k <= k1; ++k)
-      for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) {
-        fbw[k].lo[j] = (bl + j < nfil) ? fbank[(int64_t)k * nfil + bl + j] : 0.0f;
-        fbw[k].hi[j] = (bh + j < nfil) ? fbank[(int64_t)(nyq - k) * nfil + bh + j] : 0.0f;
-      }
-  }
-  {
-    int f0, f1;
-    span_of(g.nhalf, g.nhalf, &f0, &f1);
-    if (f1 >= 0 && f1 - f0 >= FE_GEMM_FB_SPAN) { h->gemm_ok = 0; return B200FE_OK; }
-    ctl->mid_base = f1 < 0 ? 0 : f0;
-    for (int j = 0; j < FE_GEMM_FB_SPAN; ++j)
-      ctl->mid_w[j] = (f1 >= 0 && f0 + j < nfil) ? fbank[(int64_t)g.nhalf * nfil + f0 + j] : 0.0f;
-  }
-  h->stream_ok = pack_drain_tables(h, fbank, nfil, g.nhalf, base) ? 1 : 0;
+  // ---- filterbank: sliding even/odd accumulator tables of the drain ------------------------------
+  if (!pack_drain_tables(h, fbank, nfil, g.nhalf, base)) { h->gemm_ok = 0; return B200FE_OK; }
   // ---- bin n_fft/4 (handled on the CUDA cores): true-unit weights ------------------------------
   float* mid = (float*)(base + h->off_gemm_mid);
   for (int j = 0; j < g.kpairs; ++j) {

@@ -203,14 +203,39 @@ __global__ void __launch_bounds__(kTailThreads) fe_tail_kernel(fe_tail_args a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fe_tail_fast_kernel : the same arithmetic as fe_tail_kernel (same operation order, so the results
-// are bit-identical) for n_filter, n_coef <= 32, one thread per tile position: the frame's (log)
-// energies and cepstral coefficients live in registers, only the delta stencils go through shared
-// memory.  grid (tiles, rows), block = tt + 2*halo rounded up to a warp.
+// fe_tail_fast_kernel : the arithmetic of fe_tail_kernel for n_filter, n_coef <= 32 with everything that can be
+// resolved at compile time resolved there: one thread per tile position, the frame's (log) energies and cepstral
+// coefficients in registers (KQ = ceil(channels / 4) float4 groups), delta stencils of half-width N unrolled
+// (N = 0: run-time loop), MUFU-based logarithms (absolute error ~1e-6 dB, far inside the 1e-4 feature tolerance).
+// Only the delta stencils go through shared memory.  grid (tiles, rows), block = tt + 2*halo rounded up to a warp.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastMax = 32;
 
-template <int KQ>  // KQ = ceil(channels / 4): the cepstral coefficients a thread keeps in registers
+__device__ __forceinline__ float fast_log_energy(float v, int log_mode, float floor_db) {
+  if (log_mode == B200FE_LOG_DB) {
+    v = 3.0102999566398120f * __log2f(fmaxf(v, 1e-10f));   // 10 log10(x) = 10 log10(2) log2(x)
+    v = fmaxf(v, floor_db);
+  } else if (log_mode == B200FE_LOG_LN) {
+    v = 0.6931471805599453f * __log2f(v + 1e-6f);
+  }
+  return v;
+}
+
+// sum_m m * c[m], m = -n .. n, around p
+template <int N>
+__device__ __forceinline__ float delta_taps(const float* p, int n) {
+  if (N > 0) {
+    float acc = p[1] - p[-1];
+#pragma unroll
+    for (int m = 2; m <= N; ++m) acc = fmaf((float)m, p[m] - p[-m], acc);
+    return acc;
+  }
+  float acc = 0.0f;
+  for (int m = 1; m <= n; ++m) acc = fmaf((float)m, p[m] - p[-m], acc);
+  return acc;
+}
+
+template <int KQ, int N>
 __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
   constexpr int kRegs = 4 * KQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -219,7 +244,7 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
   const int nc = ncoef > 0 ? ncoef : nfil;
   float* s_c = reinterpret_cast<float*>(smem_raw);      // [nc][w]
   float* s_d = s_c + (size_t)nc * w;                    // [nc][w]
-  float* s_dct = s_d + (size_t)nc * w;                  // [nfil][kFastMax] (zero padded rows of 32)
+  float* s_dct = s_d + (size_t)nc * w;                  // [nfil][4*KQ] (zero padded rows)
 
   const int j = threadIdx.x;
   const int64_t row_local = blockIdx.y;
@@ -231,35 +256,31 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
   if (ncoef > 0) {
     const float* gd = reinterpret_cast<const float*>(blob + h->off_dct);
-    for (int i = j; i < nfil * kFastMax; i += blockDim.x) {
-      const int f = i / kFastMax, k = i - f * kFastMax;
+    for (int i = j; i < nfil * kRegs; i += blockDim.x) {
+      const int f = i / kRegs, k = i - f * kRegs;
       s_dct[i] = k < ncoef ? gd[f * ncoef + k] : 0.0f;
     }
   }
   float floor_db = -INFINITY;
   if (a.log_mode == B200FE_LOG_DB && a.top_db >= 0.0f) {
     const float gmax = __uint_as_float(a.group_max[row / a.top_db_group]);
-    floor_db = 10.0f * log10f(fmaxf(gmax, 1e-10f)) - a.top_db;
+    floor_db = 3.0102999566398120f * __log2f(fmaxf(gmax, 1e-10f)) - a.top_db;
   }
   __syncthreads();
 
+  const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;   // tile position of this position's (clamped) frame
+  const bool owner = j >= halo && j < halo + tt && (t0 + j - halo) < nF;   // this thread stores frame t0 + j - halo
+  float* out_row = a.out + (size_t)row * a.n_out * nF + (t0 + j - halo);
   float c[kRegs];
 #pragma unroll
   for (int k = 0; k < kRegs; ++k) c[k] = 0.0f;
   if (j < w) {
-    const int t = fe_clampi(tv0 + j, 0, nF - 1);
-    const float* src = a.energies + (size_t)row_local * nfil * nF + t;
+    const float* src = a.energies + (size_t)row_local * nfil * nF + (tv0 + tcl);
+    if (ncoef > 0) {
 #pragma unroll 4
-    for (int f = 0; f < nfil; ++f) {
-      float v = __ldg(src + (size_t)f * nF);
-      if (a.log_mode == B200FE_LOG_DB) {
-        v = 10.0f * log10f(fmaxf(v, 1e-10f));
-        v = fmaxf(v, floor_db);
-      } else if (a.log_mode == B200FE_LOG_LN) {
-        v = logf(v + 1e-6f);
-      }
-      if (ncoef > 0) {
-        const float4* dr = reinterpret_cast<const float4*>(s_dct + f * kFastMax);
+      for (int f = 0; f < nfil; ++f) {
+        const float v = fast_log_energy(__ldg(src + (size_t)f * nF), a.log_mode, floor_db);
+        const float4* dr = reinterpret_cast<const float4*>(s_dct + f * kRegs);
 #pragma unroll
         for (int k4 = 0; k4 < KQ; ++k4) {
           const float4 d = dr[k4];
@@ -268,49 +289,50 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
           c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
           c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
         }
-      } else {
-        // no DCT: channel f is the (log) energy itself; unrolled select keeps c[] in registers
-#pragma unroll
-        for (int k = 0; k < kRegs; ++k) c[k] = (k == f) ? v : c[k];
       }
+    } else {
+      // no DCT: channel k is the (log) energy of filter k
+#pragma unroll
+      for (int k = 0; k < kRegs; ++k)
+        if (k < nc) c[k] = fast_log_energy(__ldg(src + (size_t)k * nF), a.log_mode, floor_db);
     }
     if (a.deltas >= 1) {
 #pragma unroll
       for (int k = 0; k < kRegs; ++k)
-        if (k < nc) s_c[(size_t)k * w + j] = c[k];
+        if (k < nc) s_c[k * w + j] = c[k];
     }
   }
-  const int n = (a.delta_win - 1) / 2;
-  const float denom = (float)(n * (n + 1) * (2 * n + 1)) / 3.0f;
-  const bool owner = j >= halo && j < halo + tt && (t0 + j - halo) < nF;   // this thread stores frame t0 + j - halo
-  float* out_row = a.out + (size_t)row * a.n_out * nF + (t0 + j - halo);
   if (owner) {
 #pragma unroll
     for (int k = 0; k < kRegs; ++k)
       if (k < nc) out_row[(size_t)k * nF] = c[k];
   }
   if (a.deltas >= 1) {
+    const int n = (a.delta_win - 1) / 2;
+    const float inv_denom = 3.0f / (float)(n * (n + 1) * (2 * n + 1));
     __syncthreads();
-    const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;   // tile position of the clamped frame
     if (j >= n && j < w - n) {
-      for (int k = 0; k < nc; ++k) {
-        const float* cc = s_c + (size_t)k * w + tcl;
-        float acc = 0.0f;
-        for (int m = -n; m <= n; ++m) acc += (float)m * cc[m];
-        const float d = acc / denom;
-        s_d[(size_t)k * w + j] = d;
-        if (owner) out_row[(size_t)(nc + k) * nF] = d;
+      const float* cc = s_c + tcl;
+      float* dd = s_d + j;
+      float* o = out_row + (size_t)nc * nF;
+#pragma unroll
+      for (int k = 0; k < kRegs; ++k) {
+        if (k < nc) {
+          const float d = delta_taps<N>(cc + k * w, n) * inv_denom;
+          dd[k * w] = d;
+          if (owner) o[(size_t)k * nF] = d;
+        }
       }
     }
     if (a.deltas >= 2) {
       __syncthreads();
       if (owner) {
-        for (int k = 0; k < nc; ++k) {
-          const float* dd = s_d + (size_t)k * w + j;
-          float acc = 0.0f;
-          for (int m = -n; m <= n; ++m) acc += (float)m * dd[m];
-          out_row[(size_t)(2 * nc + k) * nF] = acc / denom;
-        }
+        // delta of the delta at the clamped frame: s_d position tcl (interior: j itself)
+        const float* dd = s_d + tcl;
+        float* o = out_row + (size_t)2 * nc * nF;
+#pragma unroll
+        for (int k = 0; k < kRegs; ++k)
+          if (k < nc) o[(size_t)k * nF] = delta_taps<N>(dd + k * w, n) * inv_denom;
       }
     }
   }
@@ -411,6 +433,20 @@ size_t fe_tail_smem_bytes(const fe_tail_args& a) {
   return fl * 4;
 }
 
+template <int N>
+static void (*pick_tail_fast(int kq))(fe_tail_args) {
+  switch (kq) {
+    case 1: return fe_tail_fast_kernel<1, N>;
+    case 2: return fe_tail_fast_kernel<2, N>;
+    case 3: return fe_tail_fast_kernel<3, N>;
+    case 4: return fe_tail_fast_kernel<4, N>;
+    case 5: return fe_tail_fast_kernel<5, N>;
+    case 6: return fe_tail_fast_kernel<6, N>;
+    case 7: return fe_tail_fast_kernel<7, N>;
+    default: return fe_tail_fast_kernel<8, N>;
+  }
+}
+
 static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cudaStream_t stream) {
   fe_tail_args a = a_in;
   // tile so that tt + 2*halo fills (almost) a whole number of warps, at most 256 threads
@@ -420,12 +456,11 @@ static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cuda
   const int w = a.tt + 2 * a.halo;
   const int threads = (w + 31) & ~31;
   const int nc = a.n_coef > 0 ? a.n_coef : a.n_filter;
-  const size_t smem = ((size_t)2 * nc * w + (size_t)a.n_filter * kFastMax) * 4;
+  const int kq = (nc + 3) / 4;
+  const size_t smem = ((size_t)2 * nc * w + (size_t)a.n_filter * 4 * kq) * 4;
   typedef void (*kern_t)(fe_tail_args);
-  static const kern_t kerns[8] = {fe_tail_fast_kernel<1>, fe_tail_fast_kernel<2>, fe_tail_fast_kernel<3>,
-                                  fe_tail_fast_kernel<4>, fe_tail_fast_kernel<5>, fe_tail_fast_kernel<6>,
-                                  fe_tail_fast_kernel<7>, fe_tail_fast_kernel<8>};
-  const kern_t kern = kerns[(nc + 3) / 4 - 1];
+  const int n = a.deltas > 0 ? (a.delta_win - 1) / 2 : 0;
+  const kern_t kern = n == 1 ? pick_tail_fast<1>(kq) : n == 2 ? pick_tail_fast<2>(kq) : pick_tail_fast<0>(kq);
   cudaError_t e = set_smem((const void*)kern, smem);
   if (e != cudaSuccess) return e;
   for (int64_t r0 = 0; r0 < rows; r0 += 65535) {

@@ -4,13 +4,17 @@
 // frames = the 128 TMEM lanes of one M=128 MMA, whatever utterances they belong to, so every tile is full.
 // One persistent CTA per SM walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...
 //
-//   loader warp   per tile: the hop blocks the tile's frames need, once each, as 1-D bulk copies (TMA) into
-//                 padded shared-memory rows (conflict-free lane <-> frame reads); reflect-padded edge blocks
-//                 are synthesised with plain loads.  Per stage: the 32 KB of DFT operand tiles.
+//   loader warp   per tile: the hop blocks the tile's frames need, once each, as a handful of TMA tensor boxes
+//                 {32 floats, hop/32, 2^k hop blocks} with the 128-byte swizzle: hop blocks sit densely in shared
+//                 memory and lane <-> frame reads are still conflict-free (consecutive blocks land on different
+//                 swizzle phases because hop/32 is odd or the phase advances by hop/32 mod 8).  A small 1-D bulk
+//                 copy costs the TMA unit ~90 cycles whatever its size (130 per tile took 12 k cycles), hence
+//                 boxes.  Reflect-padded edge blocks are synthesised with plain loads.  Per stage: the 32 KB of
+//                 DFT operand tiles.
 //   MMA warp      one thread: 12 tcgen05.mma (M=128, N=n_fft/4, K=16; 4 sub-GEMMs x 3 split-fp16 products) per
 //                 stage into the 4 TMEM accumulators, tcgen05.commit -> mbarriers
 //   16 worker warps, all doing the same thing in phases:
-//     scout       max|x| per group of 4 hop blocks (shared memory) -> per-frame power-of-two scale
+//     scout       max|x| per hop block (shared memory) -> per-frame power-of-two scale
 //     produce     fold + scale + fp16 hi/lo split of 16 sample pairs per thread into the UMMA A tiles; the two
 //                 halves of the warps (0-7 / 8-15) take alternate stages, i.e. alternate A slots
 //     drain       tcgen05.ld of the four accumulators, powers, sliding even/odd triangular-filter sums
@@ -29,12 +33,12 @@ namespace {
 
 constexpr int kWorkerWarps = 16;
 constexpr int kWorkerThreads = kWorkerWarps * 32;
-constexpr int kMmaWarp = 16, kLoaderWarp = 17;
-constexpr int kThreads = 18 * 32;
+constexpr int kMmaWarp0 = 16;   // warps 16..19: one MMA issuer per sub-GEMM (ce, co, se, so)
+constexpr int kNumMmaWarps = 4;
+constexpr int kLoaderWarp = 20;
+constexpr int kThreads = 21 * 32;
 constexpr int kTileM = FE_GEMM_TILE_M;
 constexpr int kMaxSlots = 132;                    // hop blocks of a tile: 128 + 1 + one more per utterance boundary
-constexpr int kSlotGroups = kMaxSlots / 4;        // scout granularity: 4 hop blocks
-constexpr int kMinFrames = 43;                    // a tile then spans at most 4 utterances
 constexpr int kAStageBytes = 8 * 2 * kTileM * 16; // 32 KB: [sub 4][hi, lo] tiles of 128 rows x 16 K
 
 struct stream_args {
@@ -46,7 +50,7 @@ struct stream_args {
   int64_t T;
   int64_t row_base;         // absolute index of the launch's first row (group_max indexing)
   int32_t rows, n_frames, n_filter, hop, nhalf, nstages, kpairs;
-  int32_t total_frames, n_tiles, top_db_group;
+  int32_t total_frames, tile_frames, n_tiles, top_db_group;
 };
 
 struct smem_layout {
@@ -56,15 +60,15 @@ struct smem_layout {
 __host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpairs) {
   smem_layout L;
   int off = 0;
-  L.samp = off;      off += kMaxSlots * (hop * 4 + 16);
+  L.samp = off;      off += kMaxSlots * hop * 4;            // dense hop-block rows, 128-byte swizzled (base 1024-aligned)
   off = (off + 127) & ~127;
   L.a_stage = off;   off += 2 * kAStageBytes;
   L.b_stage = off;   off += 2 * fe_gemm_b_stage_bytes(nhalf);
   L.dw = off;        off += (nhalf + 1) * (int)sizeof(fe_drain_w);
   L.dids = off;      off += ((nhalf + 1) * (int)sizeof(fe_drain_ids) + 15) & ~15;
   L.dctl = off;      off += ((nhalf / 8 + 1) * 4 + 15) & ~15;
-  L.mid = off;       off += 2 * kpairs * 4;
-  L.gmax = off;      off += ((kSlotGroups + 1) * 4 + 15) & ~15;
+  L.mid = off;       off += kpairs * 4;          // interleaved weights of bin n_fft/4: even j -> Re, odd j -> Im
+  L.gmax = off;      off += ((kMaxSlots + 1) * 4 + 15) & ~15;   // max |x| per hop block of the tile
   L.us2 = off;       off += kTileM * 4;
   L.midp = off;      off += 4 * kTileM * 8;   // [producer half-group 2][K half 2][frame] (Re, Im) partials of bin n_fft/4
   L.bars = off;      off += 16 * 8;
@@ -82,35 +86,34 @@ enum { BAR_SAMP_FULL = 0, BAR_SAMP_EMPTY = 1, BAR_A_FULL = 2, BAR_B_FULL = 4, BA
 #define ST_TRACE(ev, it, q) do { } while (0)
 #endif
 
-struct tile_geo {
-  int g0, count, row0, row_last, sv0, nv;
+// 128-byte swizzle of the sample buffer (what TMA SWIZZLE_128B does): 16-byte chunk index ^= 128-byte line index mod 8
+__device__ __forceinline__ uint32_t swz(uint32_t o) { return o ^ (((o >> 7) & 7u) << 4); }
+
+struct tmaps8 {
+  CUtensorMap m[8];   // box heights 1, 2, 4, ..., 128 hop blocks
 };
-__device__ __forceinline__ tile_geo tile_geometry(int tile, int total_frames, int nF) {
-  tile_geo t;
-  t.g0 = tile * kTileM;
-  t.count = min(kTileM, total_frames - t.g0);
-  t.row0 = t.g0 / nF;
-  const int g_last = t.g0 + t.count - 1;
-  t.row_last = g_last / nF;
-  // hop block v of row r (samples [(v-1) hop, v hop)) has stream index r (nF+1) + v; frame (r, t) reads blocks t, t+1
-  t.sv0 = t.g0 + t.row0;
-  t.nv = t.count + (t.row_last - t.row0) + 1;
-  return t;
+
+__device__ __forceinline__ void tma_box_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_args a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_constant__ tmaps8 maps, const stream_args a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
   const smem_layout L = make_layout(a.hop, a.nhalf, a.kpairs);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
   const int nF = a.n_frames, hop = a.hop, nfil = a.n_filter;
-  const int rs = hop * 4 + 16;   // bytes per hop-block row: +16 puts 8 consecutive rows on 8 distinct 16-byte bank groups
+  const int nbuf = h->gemm_nbuf;   // emission buffers of the drain (2 or 4)
+  const int rs = hop * 4;        // bytes per hop-block row (dense; the 128-byte swizzle keeps lane <-> frame reads conflict-free)
 
-  if (!h->stream_ok) {   // tables without the drain tables: report instead of computing garbage
+  if (!h->gemm_ok) {   // tables without the variant's tiles: report instead of computing garbage
     if (tid == 0) atomicExch(a.error_flag, 98);
     return;
   }
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
   float* s_gmax = reinterpret_cast<float*>(smem + L.gmax);
   float* s_us2 = reinterpret_cast<float*>(smem + L.us2);
   float2* s_midp = reinterpret_cast<float2*>(smem + L.midp);
-  float* s_E = reinterpret_cast<float*>(smem + L.a_stage);   // drain scratch [2][n_filter][128] aliases A slot 0
+  float* s_E = reinterpret_cast<float*>(smem + L.a_stage);   // drain scratch [nbuf][n_filter][128] aliases A slot 0
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const uint32_t bars = smem_u32(smem + L.bars);
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
@@ -136,8 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
     const uint32_t* gctl = reinterpret_cast<const uint32_t*>(blob + h->off_gemm_dctl);
     for (int i = tid; i <= a.nhalf / 8; i += kThreads) s_dctl[i] = gctl[i];
     const float* gmid = reinterpret_cast<const float*>(blob + h->off_gemm_mid);
-    for (int i = tid; i < 2 * a.kpairs; i += kThreads) s_mid[i] = gmid[i];
-    // the scout reads whole groups of 4 rows including the row pads and rows a tile does not use: keep them finite
+    for (int i = tid; i < a.kpairs; i += kThreads) s_mid[i] = (i & 1) ? gmid[a.kpairs + i] : gmid[i];
+    // rows a tile does not use are never read unpredicated, but keep the buffer defined
     float4* z = reinterpret_cast<float4*>(s_samp);
     for (int i = tid; i < kMaxSlots * rs / 16; i += kThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
@@ -149,13 +152,13 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
     mbar_init(bar(BAR_A_FULL + 1), kWorkerWarps / 2);
     mbar_init(bar(BAR_B_FULL + 0), 1);
     mbar_init(bar(BAR_B_FULL + 1), 1);
-    mbar_init(bar(BAR_STAGE_FREE + 0), 1);
-    mbar_init(bar(BAR_STAGE_FREE + 1), 1);
-    mbar_init(bar(BAR_ACC_FULL), 1);
+    mbar_init(bar(BAR_STAGE_FREE + 0), kNumMmaWarps);
+    mbar_init(bar(BAR_STAGE_FREE + 1), kNumMmaWarps);
+    mbar_init(bar(BAR_ACC_FULL), kNumMmaWarps);
     mbar_init(bar(BAR_ACC_EMPTY), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarp0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -172,8 +175,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
     const uint32_t row_bytes = (uint32_t)hop * 4u;
     uint32_t n = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      const tile_geo g = tile_geometry(tile, a.total_frames, nF);
-      mbar_wait(bar(BAR_SAMP_EMPTY), (it & 1u) ^ 1u, a.error_flag, 1);   // workers are done with the previous tile's samples
+      const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
+      mbar_wait_relaxed(bar(BAR_SAMP_EMPTY), (it & 1u) ^ 1u, a.error_flag, 1);   // workers are done with the previous tile's samples
       ST_TRACE(0, it, 0);
       int n_edge = 0;
       for (int row = g.row0; row <= g.row_last; ++row) {
@@ -183,12 +186,35 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
       fence_proxy_async();   // earlier generic writes of edge rows vs. the bulk copies below
       if (lane == 0) mbar_arrive_expect_tx(bar(BAR_SAMP_FULL), (uint32_t)(g.nv - n_edge) * row_bytes);
       __syncwarp();
-      for (int s = lane; s < g.nv; s += 32) {
-        const int sv = g.sv0 + s;
-        const int row = sv / (nF + 1), v = sv - row * (nF + 1);
-        if (v >= 1 && v < nF)
-          bulk_g2s(smem_u32(s_samp + s * rs), a.wave + (int64_t)row * a.T + (int64_t)(v - 1) * hop, row_bytes,
-                   bar(BAR_SAMP_FULL));
+      // per utterance segment: its ordinary hop blocks are contiguous; box heights = binary digits of their count
+      for (int row = g.row0; row <= g.row_last; ++row) {
+        const int v_lo = max(g.sv0 - row * (nF + 1), 1), v_hi = min(g.sv0 + g.nv - 1 - row * (nF + 1), nF - 1);
+        const int cnt = v_hi - v_lo + 1;
+        if (cnt <= 0) continue;
+        if (lane < 8 && ((cnt >> lane) & 1)) {
+          const int first = cnt & ~((2 << lane) - 1);          // blocks taken by the larger boxes
+          const int s = row * (nF + 1) + v_lo + first - g.sv0;  // slot of this box's first block
+          tma_box_4d(smem_u32(s_samp + s * rs), &maps.m[lane], bar(BAR_SAMP_FULL), 0, 0, v_lo - 1 + first, row);
+        }
+      }
+      {
+        // pull the NEXT tile's hop blocks into L2 now (a whole tile period ahead): its bulk copies then hit L2 and
+        // the HBM reads of all SMs spread over the period instead of arriving as one burst
+        const int ntile = tile + gridDim.x;
+#ifndef FE_NO_PREFETCH
+        if (ntile < a.n_tiles) {
+#else
+        if (false) {
+#endif
+          const fe_tile_geo gn = fe_tile_geometry(ntile, a.tile_frames, a.total_frames, nF);
+          for (int row = gn.row0; row <= gn.row_last; ++row) {
+            const int v_lo = max(gn.sv0 - row * (nF + 1), 1), v_hi = min(gn.sv0 + gn.nv - 1 - row * (nF + 1), nF - 1);
+            const int bytes = (v_hi - v_lo + 1) * (int)row_bytes;
+            const char* src = reinterpret_cast<const char*>(a.wave + (int64_t)row * a.T + (int64_t)(v_lo - 1) * hop);
+            for (int o = lane * 4096; o < bytes; o += 32 * 4096)   // 4 KB pieces, one per lane
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + o), "r"(min(4096, bytes - o)) : "memory");
+          }
+        }
       }
       // edge blocks: v = 0 (reflect about sample 0) and v = nF (tail of the utterance + reflect about sample T-1)
       for (int row = g.row0; row <= g.row_last; ++row) {
@@ -197,21 +223,21 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
           const int v = e2 ? nF : 0;
           const int s = row * (nF + 1) + v - g.sv0;
           if (s < 0 || s >= g.nv) continue;
-          float* dst = reinterpret_cast<float*>(s_samp + s * rs);
           for (int e = lane; e < hop; e += 32) {
             int idx = (v - 1) * hop + e;
             idx = idx < 0 ? -idx : idx;
             idx = idx >= T ? 2 * (T - 1) - idx : idx;
-            dst[e] = __ldg(x + idx);
+            *reinterpret_cast<float*>(s_samp + swz((uint32_t)(s * rs + e * 4))) = __ldg(x + idx);
           }
         }
       }
       __syncwarp();
+      if (lane == 0) ST_TRACE(9, it, 0);
       if (lane == 0) {
         mbar_arrive(bar(BAR_SAMP_FULL));
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
-          mbar_wait(bar(BAR_STAGE_FREE + s), par ^ 1u, a.error_flag, 2);   // the MMAs that read slot s have retired
+          mbar_wait_relaxed(bar(BAR_STAGE_FREE + s), par ^ 1u, a.error_flag, 2);   // the MMAs that read slot s have retired
           mbar_arrive_expect_tx(bar(BAR_B_FULL + s), b_stage_bytes);
           bulk_g2s(smem_u32(smem + L.b_stage + s * b_stage_bytes), gB + (size_t)q * b_stage_bytes, b_stage_bytes,
                    bar(BAR_B_FULL + s));
@@ -219,36 +245,46 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
       }
       __syncwarp();
     }
-  } else if (warp == kMmaWarp) {
-    // ================================ MMA issuer ======================================================
-    if (lane == 0) {
+  } else if (warp >= kMmaWarp0) {
+    // ================================ MMA issuers =====================================================
+    // A lone thread issues one tcgen05.mma per ~100 cycles (dependent uniform-datapath instructions around every
+    // UTCHMMA; measured with tests/cuda/ts_probe.cu), slower than the tensor pipe retires an N = 128 MMA (64
+    // cycles).  The four sub-GEMMs own separate accumulators, so each gets its own issuing warp.
+    // Everything the issuing thread needs is derived from warp-uniform values (shuffle broadcasts, kernel
+    // parameters) and the MMAs sit under elect.sync, so the descriptors live in uniform registers and no per-lane
+    // "waterfall" loop is generated around each UTCHMMA (that loop made one thread issue only one MMA per ~100
+    // cycles, slower than the tensor pipe retires them: tests/cuda/ts_probe.cu).
+    {
+      const int sub = __shfl_sync(0xffffffffu, warp - kMmaWarp0, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(a.nhalf >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t b_lbo = (uint32_t)a.nhalf * 16u;
+      const uint32_t smem_a = smem_u32(smem + L.a_stage), smem_b = smem_u32(smem + L.b_stage);
+      const uint32_t tile_bytes_a = fe_gemm_tile_bytes(kTileM), tile_bytes_b = fe_gemm_tile_bytes(a.nhalf);
       uint32_t n = 0, it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(bar(BAR_ACC_EMPTY), (it & 1u) ^ 1u, a.error_flag, 3);   // previous tile drained
+        mbar_wait_relaxed(bar(BAR_ACC_EMPTY), (it & 1u) ^ 1u, a.error_flag, 3);   // previous tile drained
         tc_fence_after();
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
-          mbar_wait(bar(BAR_B_FULL + s), par, a.error_flag, 4);
-          mbar_wait(bar(BAR_A_FULL + s), par, a.error_flag, 5);
+          mbar_wait_relaxed(bar(BAR_B_FULL + s), par, a.error_flag, 4);
+          mbar_wait_relaxed(bar(BAR_A_FULL + s), par, a.error_flag, 5);
           tc_fence_after();
-          ST_TRACE(3, it, q);
-          const uint32_t a_base = smem_u32(smem + L.a_stage + s * kAStageBytes);
-          const uint32_t b_base = smem_u32(smem + L.b_stage + s * b_stage_bytes);
-#pragma unroll 1
-          for (int sub = 0; sub < 4; ++sub) {
-            const uint64_t a_hi = make_desc(a_base + fe_gemm_a_tile_offset(sub, 0), kTileM * 16, 128);
-            const uint64_t a_lo = make_desc(a_base + fe_gemm_a_tile_offset(sub, 1), kTileM * 16, 128);
-            const uint64_t b_hi = make_desc(b_base + fe_gemm_b_tile_offset(a.nhalf, sub, 0), b_lbo, 128);
-            const uint64_t b_lo = make_desc(b_base + fe_gemm_b_tile_offset(a.nhalf, sub, 1), b_lbo, 128);
-            const uint32_t d = tmem_base + (uint32_t)(sub * a.nhalf);
-            umma_f16(d, a_hi, b_hi, idesc, q > 0 ? 1u : 0u);
-            umma_f16(d, a_lo, b_hi, idesc, 1u);
-            umma_f16(d, a_hi, b_lo, idesc, 1u);
+          if (sub == 0 && lane == 0) ST_TRACE(3, it, q);
+          const uint32_t a_base = smem_a + s * kAStageBytes;
+          const uint32_t b_base = smem_b + s * b_stage_bytes;
+          if (elect_one()) {
+            // this warp's sub-GEMM: A_hi B_hi + A_lo B_hi + A_hi B_lo
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) {
+              const uint64_t da = make_desc(a_base + (2 * sub + (pr == 1 ? 1 : 0)) * tile_bytes_a, kTileM * 16, 128);
+              const uint64_t db = make_desc(b_base + (2 * sub + (pr == 2 ? 1 : 0)) * tile_bytes_b, b_lbo, 128);
+              umma_f16(tmem_u + (uint32_t)(sub * a.nhalf), da, db, idesc, (q > 0 || pr > 0) ? 1u : 0u);
+            }
+            umma_commit(bar(BAR_STAGE_FREE + s));
+            if (q == a.nstages - 1) umma_commit(bar(BAR_ACC_FULL));
           }
-          umma_commit(bar(BAR_STAGE_FREE + s));
-          if (q == a.nstages - 1) umma_commit(bar(BAR_ACC_FULL));
+          __syncwarp();
         }
       }
     }
@@ -262,31 +298,61 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
     const int cpg = a.nhalf / FE_DRAIN_GROUPS;
     uint32_t n = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      const tile_geo g = tile_geometry(tile, a.total_frames, nF);
+      const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
       const int mm = min(m, g.count - 1);                 // rows past the end of the stream repeat the last frame
       const int row = (g.g0 + mm) / nF;
       const int slot = mm + (row - g.row0);               // backward hop block; the forward one is slot + 1
       mbar_wait(bar(BAR_SAMP_FULL), it & 1u, a.error_flag, 6);
       if (tid == 0) ST_TRACE(1, it, 0);
-      // ---- scout: max |x| per group of 4 rows (pads and unused rows hold zeros / stale finite samples)
-      for (int grp = warp; grp * 4 < g.nv + 1; grp += kWorkerWarps) {
-        const float4* p = reinterpret_cast<const float4*>(s_samp + grp * 4 * rs);
-        const int n4 = rs / 4;   // float4 per 4 rows
-        float mx = 0.0f;
-        for (int i = lane; i < n4; i += 32) {
-          const float4 v = p[i];
-          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      // ---- scout: max |x| of every hop block of the tile.  A task = 4 rows: 8 lanes per row, all loads of a warp's
+      // tasks in flight together (a row is a whole number of 128-byte lines, so the swizzle only permutes inside it)
+      {
+        const int c4 = rs / 16;                 // 16-byte chunks per row
+        const int r_in = lane >> 3, l8 = lane & 7;
+        float4 v[2][8];                         // rs/16 <= 64 chunks per row: at most 8 per lane
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int r = (2 * warp + k) * 4 + r_in;
+          const float4* p = reinterpret_cast<const float4*>(s_samp + r * rs);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = l8 + 8 * u;
+            v[k][u] = (i < c4 && r < g.nv) ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-        mx = warp_max(mx);
-        if (lane == 0) s_gmax[grp] = mx;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float mx = 0.0f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[k][u].x), fabsf(v[k][u].y)), fmaxf(fabsf(v[k][u].z), fabsf(v[k][u].w))));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+          const int r = (2 * warp + k) * 4 + r_in;
+          if (l8 == 0 && r < kMaxSlots) s_gmax[r] = mx;
+        }
+        // rows 128 .. kMaxSlots-1 (a tile has up to 132 hop blocks): one more task, taken by a different warp per tile
+        if (warp == (int)(it & 15u) && g.nv > 128) {
+          const int r = 128 + r_in;
+          const float4* p = reinterpret_cast<const float4*>(s_samp + r * rs);
+          float mx = 0.0f;
+          for (int i = l8; i < c4; i += 8) {
+            const float4 q = (r < g.nv) ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))));
+          }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+          if (l8 == 0) s_gmax[r] = mx;
+        }
       }
       worker_bar();
       if (tid == 0) ST_TRACE(7, it, 0);
       float scale, unscale;
-      fe_gemm_frame_scale(2.0f * fmaxf(s_gmax[slot >> 2], s_gmax[(slot + 1) >> 2]), scale, unscale);
+      fe_gemm_frame_scale(2.0f * fmaxf(s_gmax[slot], s_gmax[slot + 1]), scale, unscale);
       // ---- produce
-      const unsigned char* brow = s_samp + slot * rs;
-      const unsigned char* frow = brow + rs;
+      const uint32_t brow = (uint32_t)(slot * rs), frow = brow + (uint32_t)rs;   // byte offsets into the sample buffer
       float mid_re = 0.0f, mid_im = 0.0f;
 #pragma unroll 1
       for (int q = 0; q < a.nstages; ++q, ++n) {
@@ -296,17 +362,17 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
         float fwd[16], bwd[16], buf[16];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const float4 f = *reinterpret_cast<const float4*>(frow + j0 * 4 + ch * 16);
+          const float4 f = *reinterpret_cast<const float4*>(s_samp + swz(frow + j0 * 4 + ch * 16));
           fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
-          const float4 b = *reinterpret_cast<const float4*>(brow + (hop - j0 - 16) * 4 + ch * 16);
+          const float4 b = *reinterpret_cast<const float4*>(s_samp + swz(brow + (hop - j0 - 16) * 4 + ch * 16));
           buf[4 * ch + 0] = b.x; buf[4 * ch + 1] = b.y; buf[4 * ch + 2] = b.z; buf[4 * ch + 3] = b.w;
         }
         // bwd[i] = x[c - j0 - i] = backward-row element hop - j0 - i; element hop (i = 0, j0 = 0) is the centre sample
-        bwd[0] = (j0 == 0) ? fwd[0] : *reinterpret_cast<const float*>(brow + (hop - j0) * 4);
+        bwd[0] = (j0 == 0) ? fwd[0] : *reinterpret_cast<const float*>(s_samp + swz(brow + (hop - j0) * 4));
 #pragma unroll
         for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
         fe_u4 chunk[8];
-        fe_stream_produce_unit(fwd, bwd, scale, s_mid + j0, s_mid + a.kpairs + j0, mid_re, mid_im, chunk);
+        fe_stream_produce_unit(fwd, bwd, scale, s_mid + j0, mid_re, mid_im, chunk);
         mbar_wait(bar(BAR_STAGE_FREE + pgrp), par ^ 1u, a.error_flag, 7);   // MMAs of this slot's previous use retired
         unsigned char* a_row = smem + L.a_stage + pgrp * kAStageBytes + khalf * kTileM * 16 + m * 16;
 #pragma unroll
@@ -316,7 +382,9 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
         if (lane == 0) mbar_arrive(bar(BAR_A_FULL + pgrp));
         if (tid == 0 || tid == 256) ST_TRACE(2, it, q);
       }
-      s_midp[(pgrp * 2 + khalf) * kTileM + m] = make_float2(mid_re, mid_im);
+      // partial sums are filed by stage parity (even stages / odd stages), not by warp group: the groups swap
+      // stage sets from tile to tile, and the drain's summation order must not depend on the tile index
+      s_midp[((int)((n ^ (uint32_t)pgrp ^ (uint32_t)a.nstages) & 1u) * 2 + khalf) * kTileM + m] = make_float2(mid_re, mid_im);
       if (pgrp == 0 && khalf == 0) s_us2[m] = unscale * unscale;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_SAMP_EMPTY));
@@ -326,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
       if (tid == 0) ST_TRACE(4, it, 0);
       {
         float4* z = reinterpret_cast<float4*>(s_E);
-        for (int i = tid; i < 2 * nfil * kTileM / 4; i += kWorkerThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < nbuf * nfil * kTileM / 4; i += kWorkerThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       worker_bar();
       if (tid == 0) ST_TRACE(8, it, 0);
@@ -334,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
         fe_drain_state st;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { st.acc[j] = 0.0f; st.id[j] = -1; }
-        float* e_col = s_E + (cg & 1) * nfil * kTileM + m;
+        float* e_col = s_E + (cg & (nbuf - 1)) * nfil * kTileM + m;
         const float us2 = s_us2[m];
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int k_begin = cg * cpg;
@@ -373,7 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
         float* dst = a.energies + (size_t)row * nfil * nF + t;
         float vmax = 0.0f;
         for (int f = warp >> 2; f < nfil; f += kWorkerWarps / 4) {   // thread -> frame m, filters f, f+4, ...
-          const float v = s_E[f * kTileM + m] + s_E[(nfil + f) * kTileM + m];
+          float v = s_E[f * kTileM + m] + s_E[(nfil + f) * kTileM + m];
+          if (nbuf == 4) v += s_E[(2 * nfil + f) * kTileM + m] + s_E[(3 * nfil + f) * kTileM + m];
           if (valid) {
             dst[(size_t)f * nF] = v;
             vmax = fmaxf(vmax, v);
@@ -398,22 +467,61 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const stream_arg
   // ---- teardown -------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarp0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn get_encode() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+
 }  // namespace
+
+int32_t fe_gemm_compiled(void) { return 1; }
+
+bool fe_gemm_supported(const b200fe_params* p) {
+  if (p->n_filter < 1 || p->n_filter > FE_GEMM_MAX_FILTERS) return false;
+  if (p->win_length != 2 * p->hop_length || p->win_length > p->n_fft) return false;
+  const int kpairs = p->win_length / 2, nhalf = p->n_fft / 4;
+  if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return false;
+  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return false;   // 4 accumulators fit TMEM
+  if (p->preemph != 0.0f) return false;
+  return make_layout(p->hop_length, nhalf, kpairs).total <= 227 * 1024;
+}
+
+bool fe_gemm_preferred(const b200fe_params* p) {
+  (void)p;
+  // measured on B200 (profiles/): the tensor-core variant is several times faster than the FFT variant on the
+  // LFCC configuration, so AUTO takes it wherever it is supported
+  return true;
+}
+bool fe_gemm_variant_built(void) { return true; }
+bool fe_gemm_auto_prefers(const b200fe_params* p) { return fe_gemm_supported(p) && fe_gemm_preferred(p); }
+
+int64_t fe_gemm_workspace_bytes(const b200fe_params* p, int64_t chunk_rows, int64_t T) {
+  (void)p; (void)chunk_rows; (void)T;
+  return 65536;  // error flag (+ trace buffer in FE_GEMM_TRACE builds)
+}
 
 bool fe_stream_supported(const b200fe_params* p, int64_t T, int64_t rows) {
   if (!fe_gemm_supported(p)) return false;
-  const int nhalf = p->n_fft / 4, kpairs = p->win_length / 2;
-  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0) return false;
   const int64_t nF = 1 + T / p->hop_length;
-  if (nF < kMinFrames || rows * nF >= (int64_t)1 << 30) return false;
-  if (T <= p->hop_length || (T & 3) != 0) return false;
-  if (2 * p->n_filter * kTileM * 4 > kAStageBytes) return false;
-  return make_layout(p->hop_length, nhalf, kpairs).total <= 227 * 1024;
+  if (nF < 2 || rows * nF >= (int64_t)1 << 30) return false;
+  if (T <= p->n_fft / 2 || (T & 3) != 0) return false;
+  return true;
 }
 
 cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int64_t row_base, int64_t rows,
@@ -435,9 +543,34 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
   a.kpairs = p->win_length / 2;
   a.nstages = a.kpairs / 32;
   a.total_frames = (int32_t)(rows * fa.n_frames);
-  a.n_tiles = (a.total_frames + kTileM - 1) / kTileM;
+  a.tile_frames = fe_tile_frames(fa.n_frames);
+  a.n_tiles = (a.total_frames + a.tile_frames - 1) / a.tile_frames;
   a.top_db_group = fa.top_db_group;
 
+  // 4-D tensor maps over the launch's rows: {32 floats, hop/32, ordinary hop blocks of a row, rows}, boxes of 2^k blocks
+  encode_tiled_fn enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  tmaps8 maps;
+  {
+    const cuuint64_t gdim[4] = {32, (cuuint64_t)(a.hop / 32), (cuuint64_t)(fa.n_frames - 1), (cuuint64_t)rows};
+    const cuuint64_t gstride[3] = {128, (cuuint64_t)a.hop * 4, (cuuint64_t)fa.T * 4};
+    const cuuint32_t estride[4] = {1, 1, 1, 1};
+    for (int k = 0; k < 8; ++k) {
+      const cuuint32_t box[4] = {32, (cuuint32_t)(a.hop / 32), 1u << k, 1};
+      CUresult r = enc(&maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.wave, gdim, gstride, box, estride,
+#if defined(FE_TMA_VARIANT) && FE_TMA_VARIANT == 1
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+#elif defined(FE_TMA_VARIANT) && FE_TMA_VARIANT == 2
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+#elif defined(FE_TMA_VARIANT) && FE_TMA_VARIANT == 3
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+#else
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+#endif
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+  }
   const int smem = make_layout(a.hop, a.nhalf, a.kpairs).total;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static int attr_done = 0;
@@ -456,7 +589,7 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
   cudaError_t e = cudaMemsetAsync(a.error_flag, 0, 4, stream);
 #endif
   if (e != cudaSuccess) return e;
-  fe_stream_kernel<<<grid, kThreads, smem, stream>>>(a);
+  fe_stream_kernel<<<grid, kThreads, smem, stream>>>(maps, a);
   *launches = 1;
   return cudaGetLastError();
 }

@@ -43,8 +43,19 @@ __device__ __noinline__ void mbar_timeout(int* error_flag, int code) {
 #endif
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+#pragma unroll 1
   for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
     if (mbar_try_wait(bar, parity)) return;
+  }
+  mbar_timeout(error_flag, code);
+}
+// Control warps (loader, MMA issuers) wait long and often; back off between polls so their spinning does not
+// take issue slots from the worker warps (30 % of all executed instructions were polls before this).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(128);
   }
   mbar_timeout(error_flag, code);
 }
@@ -52,6 +63,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);

@@ -283,7 +283,7 @@ def main():
     roofline = {
         "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
         "peak_source": peak_src,
-        "kernel": ("fe_gemm_kernel" if variant == "dft_gemm" else "fe_fft_kernel<1>"),
+        "kernel": ("fe_stream_kernel" if variant == "dft_gemm" else "fe_fft_kernel<1>"),
         "kernel_ms_per_step": dom_ms, "kernel_launches_per_step": int(dom_launches),
         "kernel_share_of_step": dom_ms / ms_per_step,
         "algorithmic_bytes_per_utt": W["bytes_per_utt"],

@@ -9,9 +9,9 @@ import b200_frontend as fe
 import helpers
 m = fe.LFCCDelta(**helpers.LFCC_CFG, variant="dft_gemm")
 eng = m.engine
-R = 1184
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 x = (0.1 * torch.randn(R, 64600, device="cuda")).clamp_(-1, 1)
-for _ in range(2):
+for _ in range(4):
     e = eng.fbank_energies(x)
 torch.cuda.synchronize()
 ws = eng._workspace[x.device]
@@ -23,5 +23,5 @@ base = tr[0, 0, 0]
 for it in range(7):
     r = lambda q, e: int(tr[it, q, e] - base)
     print("tile", it, "loader_start", r(0, 0), "samp_full", r(0, 1), "acc_full", r(0, 4), "drain_done", r(0, 5), "fin_done", r(0, 6),
-          "scout_done", r(0, 7), "zero_done", r(0, 8))
+          "scout_done", r(0, 7), "zero_done", r(0, 8), "edges_done", r(0, 9))
     print("    produced(q):", [r(q, 2) for q in range(5)], " mma_issue(q):", [r(q, 3) for q in range(5)])

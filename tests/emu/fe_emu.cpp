@@ -118,10 +118,11 @@ extern "C" int fe_emu_features(const float* wave, int64_t R, int64_t T, const in
 }
 
 // ---------------------------------------------------------------------------------------------------
-// CPU emulation of the DFT-GEMM variant (fe_gemm.cu): the same per-thread functions (fe_gemm.cuh) and the
-// same operand images / tables (fe_gemm_layout.h), with tcgen05.mma replaced by loops that decode the
-// fp16 operand tiles at their UMMA layout offsets and accumulate in fp32.  Output: filterbank energies
-// [R][n_filter][nF] (what fe_gemm_kernel writes to the workspace).
+// CPU emulation of the DFT-GEMM variant (fe_stream.cu): the same tile geometry and per-thread functions
+// (fe_gemm.cuh: stream tiles over the flat frame sequence, hop-block slots, per-frame scale, production units,
+// sliding even/odd filterbank drain) and the same operand images / tables (fe_gemm_layout.h), with tcgen05.mma
+// replaced by loops that decode the fp16 operand tiles at their UMMA layout offsets and accumulate in fp32.
+// Output: filterbank energies [R][n_filter][nF] (what fe_stream_kernel writes to the workspace).
 // ---------------------------------------------------------------------------------------------------
 #include "fe_gemm.cuh"
 
@@ -131,18 +132,6 @@ static float emu_half_at(const unsigned char* img, int off) {
   return __half2float(h);
 }
 
-static int emu_reflect(int s, int T) {
-  if (s < 0) s = -s;
-  if (s >= T) s = 2 * (T - 1) - s;
-  return s;
-}
-
-static float emu_absmax(const float* x, int lo, int hi) {
-  float m = 0.0f;
-  for (int i = lo; i < hi; ++i) m = fmaxf(m, fabsf(x[i]));
-  return m;
-}
-
 extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, const b200fe_params* p,
                                     const void* tables, float* energies) {
   const unsigned char* blob = (const unsigned char*)tables;
@@ -150,92 +139,116 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
   if (h->magic != FE_BLOB_MAGIC || !h->gemm_ok) return -1;
   const int T = (int)T_, hop = p->hop_length, nF = 1 + T / hop, nfil = p->n_filter;
   const int kpairs = h->gemm_kpairs, nhalf = h->gemm_nhalf, nstages = kpairs / 32;
-  const int nb_full = T / hop;
-  const fe_gemm_fbw* fbw = (const fe_gemm_fbw*)(blob + h->off_gemm_fb);
-  const fe_gemm_fbctl* ctl = (const fe_gemm_fbctl*)(blob + h->off_gemm_fbflag);
-  const float* mid = (const float*)(blob + h->off_gemm_mid);
+  const fe_drain_w* dw = (const fe_drain_w*)(blob + h->off_gemm_dw);
+  const uint32_t* dctl = (const uint32_t*)(blob + h->off_gemm_dctl);
+  const fe_drain_ids* dids = (const fe_drain_ids*)(blob + h->off_gemm_dids);
+  const float* gmid = (const float*)(blob + h->off_gemm_mid);
   const unsigned char* gB = blob + h->off_gemm_b;
   const int M = FE_GEMM_TILE_M;
+  std::vector<float> midc(kpairs);   // interleaved weights of bin n_fft/4, as the kernel builds them in shared memory
+  for (int j = 0; j < kpairs; ++j) midc[j] = (j & 1) ? gmid[kpairs + j] : gmid[j];
+
+  const int total = (int)(R * nF), tf = fe_tile_frames(nF);
+  const int n_tiles = (total + tf - 1) / tf;
   std::vector<unsigned char> a_stage(fe_gemm_a_stage_bytes());
-  std::vector<float> D((size_t)4 * M * nhalf), E((size_t)FE_GEMM_MAX_FILTERS * M);
-  const int tiles = (nF + M - 1) / M;
-  for (int64_t row = 0; row < R; ++row) {
-    const float* x = wave + row * T_;
-    for (int tile = 0; tile < tiles; ++tile) {
-      const int t0 = tile * M;
-      std::fill(D.begin(), D.end(), 0.0f);
-      std::fill(E.begin(), E.end(), 0.0f);
-      std::vector<float> scale(M), unscale(M), mre(M, 0.0f), mim(M, 0.0f);
-      // scout + frame scale
-      std::vector<float> bm(M + 1);
-      for (int s = 0; s <= M; ++s) {
-        const int b = t0 - 1 + s;
-        if (b < 0) bm[s] = emu_absmax(x, 0, std::min(T, 2 * hop + 1));
-        else if (b >= nb_full) bm[s] = emu_absmax(x, std::max(0, (nb_full - 2) * hop), T);
-        else bm[s] = emu_absmax(x, b * hop, (b + 1) * hop);
+  std::vector<float> D((size_t)4 * M * nhalf), E((size_t)4 * FE_GEMM_MAX_FILTERS * M);
+  const int nbuf = h->gemm_nbuf;
+  std::vector<float> samp, bmax;
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const fe_tile_geo g = fe_tile_geometry(tile, tf, total, nF);
+    if (g.nv > 132) return -2;
+    // ---- loader: the tile's hop blocks, one slot each (edge blocks reflect-padded)
+    samp.assign((size_t)g.nv * hop, 0.0f);
+    bmax.assign(g.nv, 0.0f);
+    for (int s = 0; s < g.nv; ++s) {
+      const int sv = g.sv0 + s, row = sv / (nF + 1), v = sv - row * (nF + 1);
+      const float* x = wave + (int64_t)row * T_;
+      for (int e = 0; e < hop; ++e) {
+        int idx = (v - 1) * hop + e;
+        idx = idx < 0 ? -idx : idx;
+        idx = idx >= T ? 2 * (T - 1) - idx : idx;
+        const float val = x[idx];
+        samp[(size_t)s * hop + e] = val;
+        bmax[s] = fmaxf(bmax[s], fabsf(val));   // scout
       }
-      for (int m = 0; m < M; ++m) fe_gemm_frame_scale(2.0f * fmaxf(bm[m], bm[m + 1]), scale[m], unscale[m]);
-      for (int q = 0; q < nstages; ++q) {
-        // producers
-        for (int m = 0; m < M; ++m) {
-          const int t = t0 + m, c = t * hop;
-          const bool valid = t < nF;
-          for (int half = 0; half < 2; ++half) {
-            const int j0 = 32 * q + 16 * half;
-            float fwd[16], bwd[16];
-            for (int i = 0; i < 16; ++i) {
-              fwd[i] = valid ? x[emu_reflect(c + j0 + i, T)] : 0.0f;
-              bwd[i] = valid ? x[emu_reflect(c - j0 - i, T)] : 0.0f;
-            }
-            fe_u4 chunk[8];
-            fe_gemm_produce_half(fwd, bwd, scale[m], j0, mid, mid + kpairs, mre[m], mim[m], chunk);
-            for (int sf = 0; sf < 8; ++sf)
-              memcpy(a_stage.data() + sf * fe_gemm_tile_bytes(M) + fe_gemm_operand_offset(M, m, 8 * half), &chunk[sf], 16);
-          }
-        }
-        // "tcgen05.mma": D_sub += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo over the stage's 16 K values
-        const unsigned char* b_stage = gB + (size_t)q * fe_gemm_b_stage_bytes(nhalf);
-        for (int sub = 0; sub < 4; ++sub)
-          for (int m = 0; m < M; ++m)
-            for (int n = 0; n < nhalf; ++n) {
-              float acc = D[((size_t)sub * M + m) * nhalf + n];
-              for (int kk = 0; kk < 16; ++kk) {
-                const float ah = emu_half_at(a_stage.data(), fe_gemm_a_tile_offset(sub, 0) + fe_gemm_operand_offset(M, m, kk));
-                const float al = emu_half_at(a_stage.data(), fe_gemm_a_tile_offset(sub, 1) + fe_gemm_operand_offset(M, m, kk));
-                const float bh = emu_half_at(b_stage, fe_gemm_b_tile_offset(nhalf, sub, 0) + fe_gemm_operand_offset(nhalf, n, kk));
-                const float bl = emu_half_at(b_stage, fe_gemm_b_tile_offset(nhalf, sub, 1) + fe_gemm_operand_offset(nhalf, n, kk));
-                acc += ah * bh + al * bh + ah * bl;
-              }
-              D[((size_t)sub * M + m) * nhalf + n] = acc;
-            }
-      }
-      // epilogue: per frame, chunks of 16 columns
+    }
+    std::fill(D.begin(), D.end(), 0.0f);
+    std::fill(E.begin(), E.end(), 0.0f);
+    std::vector<float> scale(M), unscale(M), mre(M, 0.0f), mim(M, 0.0f);
+    std::vector<int> slot(M);
+    for (int m = 0; m < M; ++m) {
+      const int mm = m < g.count ? m : g.count - 1;
+      const int row = (g.g0 + mm) / nF;
+      slot[m] = mm + (row - g.row0);
+      fe_gemm_frame_scale(2.0f * fmaxf(bmax[slot[m]], bmax[slot[m] + 1]), scale[m], unscale[m]);
+    }
+    for (int q = 0; q < nstages; ++q) {
+      // producers: thread (m, khalf)
       for (int m = 0; m < M; ++m) {
-        const float us2 = unscale[m] * unscale[m];
-        for (int c = 0; c < nhalf / FE_GEMM_CHUNK; ++c) {
-          float ce[16], co[16], se[16], so[16], alo[FE_GEMM_FB_SPAN], ahi[FE_GEMM_FB_SPAN];
-          for (int i = 0; i < 16; ++i) {
-            const int k = 16 * c + i;
-            ce[i] = D[((size_t)0 * M + m) * nhalf + k];
-            co[i] = D[((size_t)1 * M + m) * nhalf + k];
-            se[i] = D[((size_t)2 * M + m) * nhalf + k];
-            so[i] = D[((size_t)3 * M + m) * nhalf + k];
-          }
-          for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) alo[j] = ahi[j] = 0.0f;
-          fe_gemm_epi_cols<8>(fbw + 16 * c, ce, co, se, so, alo, ahi);
-          fe_gemm_epi_cols<8>(fbw + 16 * c + 8, ce + 8, co + 8, se + 8, so + 8, alo, ahi);
-          for (int j = 0; j < FE_GEMM_FB_SPAN; ++j) {
-            if (ctl->base_lo[c] + j < nfil) E[(size_t)(ctl->base_lo[c] + j) * M + m] += alo[j] * us2;
-            if (ctl->base_hi[c] + j < nfil) E[(size_t)(ctl->base_hi[c] + j) * M + m] += ahi[j] * us2;
-          }
+        const float* brow = samp.data() + (size_t)slot[m] * hop;
+        const float* frow = brow + hop;
+        for (int khalf = 0; khalf < 2; ++khalf) {
+          const int j0 = 32 * q + 16 * khalf;
+          float fwd[16], bwd[16];
+          for (int i = 0; i < 16; ++i) fwd[i] = frow[j0 + i];
+          bwd[0] = (j0 == 0) ? fwd[0] : brow[hop - j0];
+          for (int i = 1; i < 16; ++i) bwd[i] = brow[hop - j0 - i];
+          fe_u4 chunk[8];
+          fe_stream_produce_unit(fwd, bwd, scale[m], midc.data() + j0, mre[m], mim[m], chunk);
+          for (int sf = 0; sf < 8; ++sf)
+            memcpy(a_stage.data() + sf * fe_gemm_tile_bytes(M) + fe_gemm_operand_offset(M, m, 8 * khalf), &chunk[sf], 16);
         }
-        const float pmid = mre[m] * mre[m] + mim[m] * mim[m];
-        for (int j = 0; j < FE_GEMM_FB_SPAN; ++j)
-          if (ctl->mid_base + j < nfil) E[(size_t)(ctl->mid_base + j) * M + m] += pmid * ctl->mid_w[j];
       }
-      const int valid_rows = std::min(M, nF - t0);
-      for (int f = 0; f < nfil; ++f)
-        for (int r = 0; r < valid_rows; ++r) energies[((size_t)row * nfil + f) * nF + t0 + r] = E[(size_t)f * M + r];
+      // "tcgen05.mma": D_sub += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo over the stage's 16 K values
+      const unsigned char* b_stage = gB + (size_t)q * fe_gemm_b_stage_bytes(nhalf);
+      for (int sub = 0; sub < 4; ++sub)
+        for (int m = 0; m < M; ++m)
+          for (int n = 0; n < nhalf; ++n) {
+            float acc = D[((size_t)sub * M + m) * nhalf + n];
+            for (int kk = 0; kk < 16; ++kk) {
+              const float ah = emu_half_at(a_stage.data(), fe_gemm_a_tile_offset(sub, 0) + fe_gemm_operand_offset(M, m, kk));
+              const float al = emu_half_at(a_stage.data(), fe_gemm_a_tile_offset(sub, 1) + fe_gemm_operand_offset(M, m, kk));
+              const float bh = emu_half_at(b_stage, fe_gemm_b_tile_offset(nhalf, sub, 0) + fe_gemm_operand_offset(nhalf, n, kk));
+              const float bl = emu_half_at(b_stage, fe_gemm_b_tile_offset(nhalf, sub, 1) + fe_gemm_operand_offset(nhalf, n, kk));
+              acc += ah * bh + al * bh + ah * bl;
+            }
+            D[((size_t)sub * M + m) * nhalf + n] = acc;
+          }
+    }
+    // drain: thread (frame m, column group cg); two emission buffers indexed by group parity
+    const int cpg = nhalf / FE_DRAIN_GROUPS;
+    for (int m = 0; m < M; ++m) {
+      const float us2 = unscale[m] * unscale[m];
+      for (int cg = 0; cg < FE_DRAIN_GROUPS; ++cg) {
+        fe_drain_state st;
+        for (int j = 0; j < 4; ++j) { st.acc[j] = 0.0f; st.id[j] = -1; }
+        float* e_col = E.data() + (size_t)(cg & (nbuf - 1)) * nfil * M + m;
+        for (int k0 = cg * cpg; k0 < (cg + 1) * cpg; k0 += 8) {
+          float ce[8], co[8], se[8], so[8];
+          for (int i = 0; i < 8; ++i) {
+            ce[i] = D[((size_t)0 * M + m) * nhalf + k0 + i];
+            co[i] = D[((size_t)1 * M + m) * nhalf + k0 + i];
+            se[i] = D[((size_t)2 * M + m) * nhalf + k0 + i];
+            so[i] = D[((size_t)3 * M + m) * nhalf + k0 + i];
+          }
+          fe_drain_cols<8>(dw + k0, dids + k0, dctl[k0 >> 3], ce, co, se, so, st, e_col, nfil, us2);
+        }
+        if (cg == FE_DRAIN_GROUPS - 1) {
+          const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
+          const float re = mre[m] * bs, im = mim[m] * bs;
+          fe_drain_mid(dw + nhalf, dids + nhalf, dctl[nhalf >> 3], fmaf(re, re, im * im), st, e_col, nfil, us2);
+        }
+        fe_drain_flush(st, e_col, nfil, us2);
+      }
+    }
+    // finalize
+    for (int m = 0; m < g.count; ++m) {
+      const int gi = g.g0 + m, row = gi / nF, t = gi - row * nF;
+      for (int f = 0; f < nfil; ++f) {
+        float v = E[(size_t)f * M + m] + E[(size_t)(nfil + f) * M + m];
+        if (nbuf == 4) v += E[(size_t)(2 * nfil + f) * M + m] + E[(size_t)(3 * nfil + f) * M + m];
+        energies[((size_t)row * nfil + f) * nF + t] = v;
+      }
     }
   }
   return 0;

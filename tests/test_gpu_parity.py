@@ -352,8 +352,8 @@ def test_auto_variant_and_explicit_errors(fe):
 
 
 def test_fast_tail_equals_generic_tail(fe, monkeypatch):
-    """fe_tail_fast_kernel (registers) and fe_tail_kernel (the one the CPU emulation covers) perform the
-    same operations in the same order: identical bits."""
+    """fe_tail_fast_kernel (registers, MUFU logarithms, unrolled stencils) against fe_tail_kernel (the one the
+    CPU emulation covers): the same features to a few float32 ulps."""
     x = cuda(np.concatenate([synth.s1_noise(6), synth.s3_edge()], 0))
     for kw in (dict(deltas=2), dict(deltas=1), dict(deltas=0), dict(deltas=2, log_lf=True)):
         m = fe.LFCC(**LFCC_CFG, variant="fft", **kw)
@@ -362,9 +362,9 @@ def test_fast_tail_equals_generic_tail(fe, monkeypatch):
         monkeypatch.setenv("B200FE_GENERIC_TAIL", "1")
         generic = m(x).clone()
         monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
-        assert torch.equal(fast, generic), kw
+        assert feat_err(fast.cpu().numpy(), generic.cpu().numpy()).max() <= 1e-5, kw   # a tenth of the parity tolerance
     short = cuda(synth.s1_noise(3, 4000))
     m = fe.LFCCDelta(**LFCC_CFG, variant="fft")
     fast = m(short).clone()
     monkeypatch.setenv("B200FE_GENERIC_TAIL", "1")
-    assert torch.equal(fast, m(short))
+    assert feat_err(fast.cpu().numpy(), m(short).cpu().numpy()).max() <= 1e-5
