@@ -36,7 +36,7 @@ constexpr int kWorkerThreads = kWorkerWarps * 32;
 constexpr int kMmaWarp0 = 16;   // warps 16..19: one MMA issuer per sub-GEMM (ce, co, se, so)
 constexpr int kNumMmaWarps = 4;
 constexpr int kLoaderWarp = 20;
-constexpr int kThreads = 21 * 32;
+constexpr int kThreads = 21 * 32;  // (registers are allocated per 4 warps: 24 warps' worth -> 80 registers per thread)
 constexpr int kTileM = FE_GEMM_TILE_M;
 constexpr int kMaxSlots = 132;                    // hop blocks of a tile: 128 + 1 + one more per utterance boundary
 constexpr int kAStageBytes = 8 * 2 * kTileM * 16; // 32 KB: [sub 4][hi, lo] tiles of 128 rows x 16 K
@@ -78,7 +78,7 @@ __host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpair
 }
 
 enum { BAR_SAMP_FULL = 0, BAR_SAMP_EMPTY = 1, BAR_A_FULL = 2, BAR_B_FULL = 4, BAR_STAGE_FREE = 6, BAR_ACC_FULL = 8,
-       BAR_ACC_EMPTY = 9, BAR_COUNT = 10 };
+       BAR_ACC_EMPTY = 9, BAR_SCOUT_FULL = 10, BAR_ZERO_DONE = 11, BAR_COUNT = 12 };
 
 #ifdef FE_GEMM_TRACE
 #define ST_TRACE(ev, it, q) do { if (blockIdx.x == 0 && (it) < 8) { ((long long*)(a.error_flag + 64))[((it) * 8 + (q)) * 16 + (ev)] = clock64(); } } while (0)
@@ -98,6 +98,31 @@ __device__ __forceinline__ void tma_box_4d(uint32_t dst, const CUtensorMap* map,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// max |x| of every hop block of a tile, by `nwarps` warps (this one is `w`): 8 lanes per row, 4 rows per pass (a row
+// is a whole number of 128-byte lines, so the swizzle only permutes inside it)
+__device__ __forceinline__ void scout_rows(const unsigned char* s_samp, float* s_gmax, int rs, int nv, int w, int nwarps, int lane) {
+  const int c4 = rs / 16;                 // 16-byte chunks per row
+  const int r_in = lane >> 3, l8 = lane & 7;
+  for (int r0 = 4 * w; r0 < nv; r0 += 4 * nwarps) {
+    const int r = r0 + r_in;
+    const float4* p = reinterpret_cast<const float4*>(s_samp + r * rs);
+    float4 v[8];                          // rs/16 <= 64 chunks per row: at most 8 per lane, all in flight together
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = l8 + 8 * u;
+      v[u] = (i < c4 && r < nv) ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float mx = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    if (l8 == 0 && r < nv) s_gmax[r] = mx;
+  }
 }
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
@@ -156,6 +181,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
     mbar_init(bar(BAR_STAGE_FREE + 1), kNumMmaWarps);
     mbar_init(bar(BAR_ACC_FULL), kNumMmaWarps);
     mbar_init(bar(BAR_ACC_EMPTY), 1);
+    mbar_init(bar(BAR_SCOUT_FULL), kNumMmaWarps);
+    mbar_init(bar(BAR_ZERO_DONE), kNumMmaWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp0) {
@@ -197,25 +224,6 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           tma_box_4d(smem_u32(s_samp + s * rs), &maps.m[lane], bar(BAR_SAMP_FULL), 0, 0, v_lo - 1 + first, row);
         }
       }
-      {
-        // pull the NEXT tile's hop blocks into L2 now (a whole tile period ahead): its bulk copies then hit L2 and
-        // the HBM reads of all SMs spread over the period instead of arriving as one burst
-        const int ntile = tile + gridDim.x;
-#ifndef FE_NO_PREFETCH
-        if (ntile < a.n_tiles) {
-#else
-        if (false) {
-#endif
-          const fe_tile_geo gn = fe_tile_geometry(ntile, a.tile_frames, a.total_frames, nF);
-          for (int row = gn.row0; row <= gn.row_last; ++row) {
-            const int v_lo = max(gn.sv0 - row * (nF + 1), 1), v_hi = min(gn.sv0 + gn.nv - 1 - row * (nF + 1), nF - 1);
-            const int bytes = (v_hi - v_lo + 1) * (int)row_bytes;
-            const char* src = reinterpret_cast<const char*>(a.wave + (int64_t)row * a.T + (int64_t)(v_lo - 1) * hop);
-            for (int o = lane * 4096; o < bytes; o += 32 * 4096)   // 4 KB pieces, one per lane
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + o), "r"(min(4096, bytes - o)) : "memory");
-          }
-        }
-      }
       // edge blocks: v = 0 (reflect about sample 0) and v = nF (tail of the utterance + reflect about sample T-1)
       for (int row = g.row0; row <= g.row_last; ++row) {
         const float* x = a.wave + (int64_t)row * a.T;
@@ -223,18 +231,26 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           const int v = e2 ? nF : 0;
           const int s = row * (nF + 1) + v - g.sv0;
           if (s < 0 || s >= g.nv) continue;
-          for (int e = lane; e < hop; e += 32) {
+          float val[8];   // hop <= 256: at most 8 elements per lane, all loads in flight before the first store
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int e = lane + 32 * u;
             int idx = (v - 1) * hop + e;
             idx = idx < 0 ? -idx : idx;
             idx = idx >= T ? 2 * (T - 1) - idx : idx;
-            *reinterpret_cast<float*>(s_samp + swz((uint32_t)(s * rs + e * 4))) = __ldg(x + idx);
+            val[u] = e < hop ? __ldg(x + idx) : 0.0f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int e = lane + 32 * u;
+            if (e < hop) *reinterpret_cast<float*>(s_samp + swz((uint32_t)(s * rs + e * 4))) = val[u];
           }
         }
       }
       __syncwarp();
       if (lane == 0) ST_TRACE(9, it, 0);
+      if (lane == 0) mbar_arrive(bar(BAR_SAMP_FULL));
       if (lane == 0) {
-        mbar_arrive(bar(BAR_SAMP_FULL));
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
           mbar_wait_relaxed(bar(BAR_STAGE_FREE + s), par ^ 1u, a.error_flag, 2);   // the MMAs that read slot s have retired
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
     // "waterfall" loop is generated around each UTCHMMA (that loop made one thread issue only one MMA per ~100
     // cycles, slower than the tensor pipe retires them: tests/cuda/ts_probe.cu).
     {
-      const int sub = __shfl_sync(0xffffffffu, warp - kMmaWarp0, 0);
+      const int sub0 = (4 / kNumMmaWarps) * __shfl_sync(0xffffffffu, warp - kMmaWarp0, 0);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(a.nhalf >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t b_lbo = (uint32_t)a.nhalf * 16u;
@@ -263,6 +279,14 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       const uint32_t tile_bytes_a = fe_gemm_tile_bytes(kTileM), tile_bytes_b = fe_gemm_tile_bytes(a.nhalf);
       uint32_t n = 0, it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        // scout: this tile's samples land while the workers still drain the previous tile; these warps are idle then
+        {
+          const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
+          mbar_wait_relaxed(bar(BAR_SAMP_FULL), it & 1u, a.error_flag, 10);
+          scout_rows(s_samp, s_gmax, rs, g.nv, warp - kMmaWarp0, kNumMmaWarps, lane);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL));
+        }
         mbar_wait_relaxed(bar(BAR_ACC_EMPTY), (it & 1u) ^ 1u, a.error_flag, 3);   // previous tile drained
         tc_fence_after();
         for (int q = 0; q < a.nstages; ++q, ++n) {
@@ -270,22 +294,36 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           mbar_wait_relaxed(bar(BAR_B_FULL + s), par, a.error_flag, 4);
           mbar_wait_relaxed(bar(BAR_A_FULL + s), par, a.error_flag, 5);
           tc_fence_after();
-          if (sub == 0 && lane == 0) ST_TRACE(3, it, q);
+          if (sub0 == 0 && lane == 0) ST_TRACE(3, it, q);
           const uint32_t a_base = smem_a + s * kAStageBytes;
           const uint32_t b_base = smem_b + s * b_stage_bytes;
           if (elect_one()) {
-            // this warp's sub-GEMM: A_hi B_hi + A_lo B_hi + A_hi B_lo
+            // this warp's sub-GEMM(s): A_hi B_hi + A_lo B_hi + A_hi B_lo, alternating accumulators if it has two
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr) {
-              const uint64_t da = make_desc(a_base + (2 * sub + (pr == 1 ? 1 : 0)) * tile_bytes_a, kTileM * 16, 128);
-              const uint64_t db = make_desc(b_base + (2 * sub + (pr == 2 ? 1 : 0)) * tile_bytes_b, b_lbo, 128);
-              umma_f16(tmem_u + (uint32_t)(sub * a.nhalf), da, db, idesc, (q > 0 || pr > 0) ? 1u : 0u);
+#pragma unroll
+              for (int ds = 0; ds < 4 / kNumMmaWarps; ++ds) {
+                const int sub = sub0 + ds;
+                const uint64_t da = make_desc(a_base + (2 * sub + (pr == 1 ? 1 : 0)) * tile_bytes_a, kTileM * 16, 128);
+                const uint64_t db = make_desc(b_base + (2 * sub + (pr == 2 ? 1 : 0)) * tile_bytes_b, b_lbo, 128);
+                umma_f16(tmem_u + (uint32_t)(sub * a.nhalf), da, db, idesc, (q > 0 || pr > 0) ? 1u : 0u);
+              }
             }
             umma_commit(bar(BAR_STAGE_FREE + s));
             if (q == a.nstages - 1) umma_commit(bar(BAR_ACC_FULL));
           }
           __syncwarp();
         }
+        // the drain scratch aliases A slot 0: clear it as soon as the tile's MMAs (its last readers) have retired,
+        // while the workers already load their first accumulator columns
+        mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 11);
+        {
+          float4* z = reinterpret_cast<float4*>(s_E);
+          for (int i = (warp - kMmaWarp0) * 32 + lane; i < nbuf * nfil * kTileM / 4; i += kNumMmaWarps * 32)
+            z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_ZERO_DONE));
       }
     }
   } else {
@@ -304,49 +342,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       const int slot = mm + (row - g.row0);               // backward hop block; the forward one is slot + 1
       mbar_wait(bar(BAR_SAMP_FULL), it & 1u, a.error_flag, 6);
       if (tid == 0) ST_TRACE(1, it, 0);
-      // ---- scout: max |x| of every hop block of the tile.  A task = 4 rows: 8 lanes per row, all loads of a warp's
-      // tasks in flight together (a row is a whole number of 128-byte lines, so the swizzle only permutes inside it)
-      {
-        const int c4 = rs / 16;                 // 16-byte chunks per row
-        const int r_in = lane >> 3, l8 = lane & 7;
-        float4 v[2][8];                         // rs/16 <= 64 chunks per row: at most 8 per lane
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int r = (2 * warp + k) * 4 + r_in;
-          const float4* p = reinterpret_cast<const float4*>(s_samp + r * rs);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = l8 + 8 * u;
-            v[k][u] = (i < c4 && r < g.nv) ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          float mx = 0.0f;
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[k][u].x), fabsf(v[k][u].y)), fmaxf(fabsf(v[k][u].z), fabsf(v[k][u].w))));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-          const int r = (2 * warp + k) * 4 + r_in;
-          if (l8 == 0 && r < kMaxSlots) s_gmax[r] = mx;
-        }
-        // rows 128 .. kMaxSlots-1 (a tile has up to 132 hop blocks): one more task, taken by a different warp per tile
-        if (warp == (int)(it & 15u) && g.nv > 128) {
-          const int r = 128 + r_in;
-          const float4* p = reinterpret_cast<const float4*>(s_samp + r * rs);
-          float mx = 0.0f;
-          for (int i = l8; i < c4; i += 8) {
-            const float4 q = (r < g.nv) ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))));
-          }
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-          if (l8 == 0) s_gmax[r] = mx;
-        }
-      }
+      // the MMA warps have scouted the tile's hop blocks (max |x| each) while these warps drained the previous one
+      mbar_wait(bar(BAR_SCOUT_FULL), it & 1u, a.error_flag, 9);
       worker_bar();
       if (tid == 0) ST_TRACE(7, it, 0);
       float scale, unscale;
@@ -364,7 +361,9 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         for (int ch = 0; ch < 4; ++ch) {
           const float4 f = *reinterpret_cast<const float4*>(s_samp + swz(frow + j0 * 4 + ch * 16));
           fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
-          const float4 b = *reinterpret_cast<const float4*>(s_samp + swz(brow + (hop - j0 - 16) * 4 + ch * 16));
+          float4 b;   // asm: keeps the 16-byte load whole even where only three of its elements are used
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                       : "r"(smem_u32(s_samp) + swz(brow + (hop - j0 - 16) * 4 + ch * 16)));
           buf[4 * ch + 0] = b.x; buf[4 * ch + 1] = b.y; buf[4 * ch + 2] = b.z; buf[4 * ch + 3] = b.w;
         }
         // bwd[i] = x[c - j0 - i] = backward-row element hop - j0 - i; element hop (i = 0, j0 = 0) is the centre sample
@@ -393,12 +392,6 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       tc_fence_after();
       if (tid == 0) ST_TRACE(4, it, 0);
       {
-        float4* z = reinterpret_cast<float4*>(s_E);
-        for (int i = tid; i < nbuf * nfil * kTileM / 4; i += kWorkerThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      worker_bar();
-      if (tid == 0) ST_TRACE(8, it, 0);
-      {
         fe_drain_state st;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { st.acc[j] = 0.0f; st.id[j] = -1; }
@@ -406,6 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         const float us2 = s_us2[m];
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int k_begin = cg * cpg;
+        bool scratch_ready = false;
 #pragma unroll 1
         for (int k0 = k_begin; k0 < k_begin + cpg; k0 += 8) {
           float ce[8], co[8], se[8], so[8];
@@ -414,7 +408,12 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           tmem_ld8(tbase + (uint32_t)(2 * a.nhalf + k0), se);
           tmem_ld8(tbase + (uint32_t)(3 * a.nhalf + k0), so);
           const unsigned ctl = s_dctl[k0 >> 3];
+          if (!scratch_ready) {   // the MMA warps clear the emission scratch while the first columns are being loaded
+            mbar_wait(bar(BAR_ZERO_DONE), it & 1u, a.error_flag, 12);
+            scratch_ready = true;
+          }
           tmem_ld_wait();
+          tmem_ld_tie8(ce); tmem_ld_tie8(co); tmem_ld_tie8(se); tmem_ld_tie8(so);
           fe_drain_cols<8>(s_dw + k0, s_dids + k0, ctl, ce, co, se, so, st, e_col, nfil, us2);
         }
         if (cg == FE_DRAIN_GROUPS - 1) {
@@ -427,6 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           fe_drain_mid(s_dw + a.nhalf, s_dids + a.nhalf, s_dctl[a.nhalf >> 3], fmaf(re, re, im * im), st, e_col, nfil, us2);
         }
         fe_drain_flush(st, e_col, nfil, us2);
+        if (tid == 0) ST_TRACE(12, it, 0);
       }
       tc_fence_before();
       worker_bar();

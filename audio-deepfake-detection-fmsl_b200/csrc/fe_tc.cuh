@@ -119,6 +119,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Ties 8 registers loaded by an earlier tcgen05.ld to a point AFTER the wait: the compiler sees the registers as
+// written here, so no use of them can be scheduled above the wait (volatile asm statements keep their order).
+__device__ __forceinline__ void tmem_ld_tie8(float* v) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
