@@ -235,16 +235,16 @@ __device__ __forceinline__ float delta_taps(const float* p, int n) {
   return acc;
 }
 
-template <int KQ, int N>
+template <int KQ, int N, bool EXACT>   // EXACT: the channel count is exactly 4*KQ (no per-channel bound checks)
 __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
   constexpr int kRegs = 4 * KQ;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tt = a.tt, halo = a.halo, w = tt + 2 * halo;
   const int nfil = a.n_filter, ncoef = a.n_coef;
-  const int nc = ncoef > 0 ? ncoef : nfil;
+  const int nc = EXACT ? kRegs : (ncoef > 0 ? ncoef : nfil);
   float* s_c = reinterpret_cast<float*>(smem_raw);      // [nc][w]
-  float* s_d = s_c + (size_t)nc * w;                    // [nc][w]
-  float* s_dct = s_d + (size_t)nc * w;                  // [nfil][4*KQ] (zero padded rows)
+  float* s_d = s_c + nc * w;                            // [nc][w]
+  float* s_dct = s_d + nc * w;                          // [nfil][4*KQ] (zero padded rows)
 
   const int j = threadIdx.x;
   const int64_t row_local = blockIdx.y;
@@ -270,17 +270,17 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
 
   const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;   // tile position of this position's (clamped) frame
   const bool owner = j >= halo && j < halo + tt && (t0 + j - halo) < nF;   // this thread stores frame t0 + j - halo
-  float* out_row = a.out + (size_t)row * a.n_out * nF + (t0 + j - halo);
+  float* out_p = a.out + (size_t)row * a.n_out * nF + (t0 + j - halo);    // walks down the channels
   float c[kRegs];
 #pragma unroll
   for (int k = 0; k < kRegs; ++k) c[k] = 0.0f;
   if (j < w) {
     const float* src = a.energies + (size_t)row_local * nfil * nF + (tv0 + tcl);
     if (ncoef > 0) {
+      const float4* dr = reinterpret_cast<const float4*>(s_dct);
 #pragma unroll 4
-      for (int f = 0; f < nfil; ++f) {
-        const float v = fast_log_energy(__ldg(src + (size_t)f * nF), a.log_mode, floor_db);
-        const float4* dr = reinterpret_cast<const float4*>(s_dct + f * kRegs);
+      for (int f = 0; f < nfil; ++f, src += nF, dr += KQ) {
+        const float v = fast_log_energy(__ldg(src), a.log_mode, floor_db);
 #pragma unroll
         for (int k4 = 0; k4 < KQ; ++k4) {
           const float4 d = dr[k4];
@@ -294,18 +294,20 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
       // no DCT: channel k is the (log) energy of filter k
 #pragma unroll
       for (int k = 0; k < kRegs; ++k)
-        if (k < nc) c[k] = fast_log_energy(__ldg(src + (size_t)k * nF), a.log_mode, floor_db);
+        if (EXACT || k < nc) c[k] = fast_log_energy(__ldg(src + (size_t)k * nF), a.log_mode, floor_db);
     }
     if (a.deltas >= 1) {
+      float* sc = s_c + j;
 #pragma unroll
       for (int k = 0; k < kRegs; ++k)
-        if (k < nc) s_c[k * w + j] = c[k];
+        if (EXACT || k < nc) sc[k * w] = c[k];
     }
   }
   if (owner) {
+    float* o = out_p;
 #pragma unroll
-    for (int k = 0; k < kRegs; ++k)
-      if (k < nc) out_row[(size_t)k * nF] = c[k];
+    for (int k = 0; k < kRegs; ++k, o += nF)
+      if (EXACT || k < nc) *o = c[k];
   }
   if (a.deltas >= 1) {
     const int n = (a.delta_win - 1) / 2;
@@ -314,13 +316,13 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
     if (j >= n && j < w - n) {
       const float* cc = s_c + tcl;
       float* dd = s_d + j;
-      float* o = out_row + (size_t)nc * nF;
+      float* o = out_p + (size_t)nc * nF;
 #pragma unroll
-      for (int k = 0; k < kRegs; ++k) {
-        if (k < nc) {
-          const float d = delta_taps<N>(cc + k * w, n) * inv_denom;
-          dd[k * w] = d;
-          if (owner) o[(size_t)k * nF] = d;
+      for (int k = 0; k < kRegs; ++k, cc += w, dd += w, o += nF) {
+        if (EXACT || k < nc) {
+          const float d = delta_taps<N>(cc, n) * inv_denom;
+          *dd = d;
+          if (owner) *o = d;
         }
       }
     }
@@ -329,10 +331,10 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
       if (owner) {
         // delta of the delta at the clamped frame: s_d position tcl (interior: j itself)
         const float* dd = s_d + tcl;
-        float* o = out_row + (size_t)2 * nc * nF;
+        float* o = out_p + (size_t)2 * nc * nF;
 #pragma unroll
-        for (int k = 0; k < kRegs; ++k)
-          if (k < nc) o[(size_t)k * nF] = delta_taps<N>(dd + k * w, n) * inv_denom;
+        for (int k = 0; k < kRegs; ++k, dd += w, o += nF)
+          if (EXACT || k < nc) *o = delta_taps<N>(dd, n) * inv_denom;
       }
     }
   }
@@ -433,17 +435,17 @@ size_t fe_tail_smem_bytes(const fe_tail_args& a) {
   return fl * 4;
 }
 
-template <int N>
+template <int N, bool EXACT>
 static void (*pick_tail_fast(int kq))(fe_tail_args) {
   switch (kq) {
-    case 1: return fe_tail_fast_kernel<1, N>;
-    case 2: return fe_tail_fast_kernel<2, N>;
-    case 3: return fe_tail_fast_kernel<3, N>;
-    case 4: return fe_tail_fast_kernel<4, N>;
-    case 5: return fe_tail_fast_kernel<5, N>;
-    case 6: return fe_tail_fast_kernel<6, N>;
-    case 7: return fe_tail_fast_kernel<7, N>;
-    default: return fe_tail_fast_kernel<8, N>;
+    case 1: return fe_tail_fast_kernel<1, N, EXACT>;
+    case 2: return fe_tail_fast_kernel<2, N, EXACT>;
+    case 3: return fe_tail_fast_kernel<3, N, EXACT>;
+    case 4: return fe_tail_fast_kernel<4, N, EXACT>;
+    case 5: return fe_tail_fast_kernel<5, N, EXACT>;
+    case 6: return fe_tail_fast_kernel<6, N, EXACT>;
+    case 7: return fe_tail_fast_kernel<7, N, EXACT>;
+    default: return fe_tail_fast_kernel<8, N, EXACT>;
   }
 }
 
@@ -460,7 +462,9 @@ static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cuda
   const size_t smem = ((size_t)2 * nc * w + (size_t)a.n_filter * 4 * kq) * 4;
   typedef void (*kern_t)(fe_tail_args);
   const int n = a.deltas > 0 ? (a.delta_win - 1) / 2 : 0;
-  const kern_t kern = n == 1 ? pick_tail_fast<1>(kq) : n == 2 ? pick_tail_fast<2>(kq) : pick_tail_fast<0>(kq);
+  const bool exact = nc == 4 * kq;
+  const kern_t kern = exact ? (n == 1 ? pick_tail_fast<1, true>(kq) : n == 2 ? pick_tail_fast<2, true>(kq) : pick_tail_fast<0, true>(kq))
+                            : (n == 1 ? pick_tail_fast<1, false>(kq) : n == 2 ? pick_tail_fast<2, false>(kq) : pick_tail_fast<0, false>(kq));
   cudaError_t e = set_smem((const void*)kern, smem);
   if (e != cudaSuccess) return e;
   for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
