@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) ts_probe_kernel(args a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(a.mode == 2 ? 2 : 1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -88,17 +88,14 @@ __global__ void __launch_bounds__(128) ts_probe_kernel(args a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // issue modes: 0 = one thread (lane 0 of warp 1) issues everything; 1 = the same under elect.sync (warp-uniform
-  // control flow); 2 = warps 1 and 2 each issue the MMAs of their own accumulator (nacc must be 2), elect.sync
-  const bool issuer = (a.mode == 2) ? (warp == 1 || warp == 2) : (warp == 1);
-  if (issuer) {
-    uint32_t elected = (lane == 0);
-    if (a.mode >= 1) {
-      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
-    }
+  // issue: warp 1, warp-uniform control flow, operands from uniform values, MMAs under elect.sync (the way the
+  // kernel issues them): measures what the tensor pipe itself sustains.  nacc accumulators are cycled round-robin.
+  if (warp == 1) {
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
     const int N = a.nslice;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int j_lo = a.mode == 2 ? warp - 1 : 0, j_hi = a.mode == 2 ? warp : a.nacc;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sB_u = smem_u32(sB), sA_u = smem_u32(sA);
     const long long t0 = clock64();
     if (elected) {
@@ -106,22 +103,22 @@ __global__ void __launch_bounds__(128) ts_probe_kernel(args a) {
         for (int n0 = 0; n0 < NB; n0 += N) {
 #pragma unroll
           for (int s = 0; s < KSTEPS; ++s) {
-            for (int j = j_lo; j < j_hi; ++j) {
+            for (int j = 0; j < a.nacc; ++j) {
               const uint64_t db = make_desc(sB_u + s * 4096 + n0 * 16, 2048, 128);
               const uint32_t acc = s > 0 ? 1u : 0u;
-              const uint32_t d = tmem_base + n0 + j * NB;
+              const uint32_t d = tb + n0 + j * NB;
               if (a.a_in_tmem) {
-                const uint32_t at = tmem_base + a_col0 + 8 * s;
+                const uint32_t at = tb + a_col0 + 8 * s;
                 asm volatile(
                     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
-                    "r"(at), "l"(db), "r"(idesc), "r"(acc));
+                    "r"(at), "l"(db), "r"(idesc), "r"(acc) : "memory");
               } else {
                 const uint64_t da = make_desc(sA_u + s * 4096, 2048, 128);
                 asm volatile(
                     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
-                    "l"(da), "l"(db), "r"(idesc), "r"(acc));
+                    "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
               }
             }
           }
@@ -140,7 +137,7 @@ __global__ void __launch_bounds__(128) ts_probe_kernel(args a) {
             : "memory");
       }
       const long long t2 = clock64();
-      if (warp == 1) { a.cyc[0] = t1 - t0; a.cyc[1] = t2 - t0; }
+      a.cyc[0] = t1 - t0; a.cyc[1] = t2 - t0;
       if (!ok) *a.status = 1;
     }
   }
@@ -196,12 +193,11 @@ int main() {
   CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
   const int smem = 2 * KSTEPS * 4096 + 1024;
   CK(cudaFuncSetAttribute(ts_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  for (int a_in_tmem = 1; a_in_tmem < 2; ++a_in_tmem)
-    for (int N : {128, 32})
-      for (int mode : {0, 1, 2})
-      for (int nacc : {1, 2})
+  for (int a_in_tmem = 0; a_in_tmem < 2; ++a_in_tmem)
+    for (int N : {128, 64, 32})
+      for (int mode : {1})
+      for (int nacc : {1, 2, 3})
       for (int reps : {64}) {
-        if (mode == 2 && nacc != 2) continue;
         CK(cudaMemset(dD, 0xff, 128 * NB * 4));
         CK(cudaMemset(dS, 0, 4));
         args a{dA, dB, dD, dC, dS, N, a_in_tmem, reps, mode, nacc};
