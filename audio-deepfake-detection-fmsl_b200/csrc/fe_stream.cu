@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       // ---- drain
       mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 8);
       tc_fence_after();
+      worker_bar();   // every worker's s_midp / s_us2 entries of the tile are written before any drain thread reads them
       if (tid == 0) ST_TRACE(4, it, 0);
       {
         fe_drain_state st;
