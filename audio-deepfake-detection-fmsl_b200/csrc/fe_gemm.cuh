@@ -136,22 +136,21 @@ FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scal
 // ---- drain: sliding even/odd filter accumulators (tables: fe_gemm_layout.h) ------------------------------
 struct fe_drain_state {
   float acc[4];
-  int id[4];
+  int off[4];   // element offset of the accumulator's filter row in the emission scratch (dummy row: none)
 };
 
-// adds one finished accumulator to the frame's filter sum (e_col = this frame's column of the [filter][128] array)
-FE_HD void fe_drain_emit(float* e_col, int nfil, int id, float v, float us2) {
-  if (id >= 0 && id < nfil) e_col[id * FE_GEMM_TILE_M] = fmaf(v, us2, e_col[id * FE_GEMM_TILE_M]);
-}
+// adds one finished accumulator to the frame's filter sum (e_col = this frame's column of the [filter + 1][128] array;
+// accumulators without a filter point at the dummy last row, so there is nothing to test)
+FE_HD void fe_drain_emit(float* e_col, int off, float v, float us2) { e_col[off] = fmaf(v, us2, e_col[off]); }
 
 // the (rare, thread-uniform) switches of one column
-FE_HD void fe_drain_switch(unsigned flags, fe_drain_ids ids, fe_drain_state& st, float* e_col, int nfil, float us2) {
+FE_HD void fe_drain_switch(unsigned flags, fe_drain_ids ids, fe_drain_state& st, float* e_col, float us2) {
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     if (flags & (1u << a)) {
-      fe_drain_emit(e_col, nfil, st.id[a], st.acc[a], us2);
+      fe_drain_emit(e_col, st.off[a], st.acc[a], us2);
       st.acc[a] = 0.0f;
-      st.id[a] = ids.id[a];
+      st.off[a] = ids.off[a];
     }
   }
 }
@@ -159,14 +158,14 @@ FE_HD void fe_drain_switch(unsigned flags, fe_drain_ids ids, fe_drain_state& st,
 // NB consecutive columns starting at a multiple of 8 (ctl = the batch's switch word, w / ids at the first column)
 template <int NB>
 FE_HD void fe_drain_cols(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, const float* ce, const float* co,
-                         const float* se, const float* so, fe_drain_state& st, float* e_col, int nfil, float us2) {
+                         const float* se, const float* so, fe_drain_state& st, float* e_col, float us2) {
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const float re1 = ce[i] + co[i], im1 = se[i] + so[i], re2 = ce[i] - co[i], im2 = so[i] - se[i];
     const float p1 = fmaf(re1, re1, im1 * im1);  // |X[k]|^2 (scaled units)
     const float p2 = fmaf(re2, re2, im2 * im2);  // |X[n_fft/2 - k]|^2
     const unsigned fl = (ctl >> (4 * i)) & 15u;
-    if (fl) fe_drain_switch(fl, ids[i], st, e_col, nfil, us2);
+    if (fl) fe_drain_switch(fl, ids[i], st, e_col, us2);
     const fe_drain_w t = w[i];
     st.acc[0] = fmaf(p1, t.w[0], st.acc[0]);
     st.acc[1] = fmaf(p1, t.w[1], st.acc[1]);
@@ -177,16 +176,16 @@ FE_HD void fe_drain_cols(const fe_drain_w* w, const fe_drain_ids* ids, unsigned 
 
 // bin n_fft/4 (column index nhalf of the tables): only the lo-run accumulators
 FE_HD void fe_drain_mid(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, float p_mid, fe_drain_state& st,
-                        float* e_col, int nfil, float us2) {
+                        float* e_col, float us2) {
   const unsigned fl = ctl & 3u;
-  if (fl) fe_drain_switch(fl, ids[0], st, e_col, nfil, us2);
+  if (fl) fe_drain_switch(fl, ids[0], st, e_col, us2);
   st.acc[0] = fmaf(p_mid, w[0].w[0], st.acc[0]);
   st.acc[1] = fmaf(p_mid, w[0].w[1], st.acc[1]);
 }
 
-FE_HD void fe_drain_flush(fe_drain_state& st, float* e_col, int nfil, float us2) {
+FE_HD void fe_drain_flush(fe_drain_state& st, float* e_col, float us2) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) fe_drain_emit(e_col, nfil, st.id[a], st.acc[a], us2);
+  for (int a = 0; a < 4; ++a) fe_drain_emit(e_col, st.off[a], st.acc[a], us2);
 }
 
 #endif  // FE_GEMM_CUH_

@@ -33,7 +33,8 @@ struct alignas(16) fe_drain_w {
   float w[4];        // weights of bin k for (lo even, lo odd) and of bin n_fft/2 - k for (hi even, hi odd)
 };
 struct fe_drain_ids {
-  int8_t id[4];      // filter of each accumulator once this column's switches are done (-1: none yet)
+  int16_t off[4];    // per accumulator, once this column's switches are done: element offset (filter * 128) of its
+                     // filter's row in the frame-major emission scratch; n_filter * 128 (a dummy row) while it has none
 };
 #define FE_DRAIN_GROUPS 4   // column groups (warps per TMEM lane quarter)
 

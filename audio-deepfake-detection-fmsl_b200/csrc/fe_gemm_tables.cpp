@@ -96,7 +96,7 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
           if (f != cur[a]) { flags |= 1u << a; cur[a] = f; }
         }
       }
-      for (int a = 0; a < 4; ++a) dids[k].id[a] = (int8_t)cur[a];
+      for (int a = 0; a < 4; ++a) dids[k].off[a] = (int16_t)((cur[a] < 0 ? nfil : cur[a]) * FE_GEMM_TILE_M);
       dctl[k / 8] |= flags << (4 * (k % 8));
     }
   }
@@ -111,7 +111,7 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
     if (m != low && m != (low | (low << 1))) adjacent_only = false;
   }
   h->gemm_nbuf = adjacent_only ? 2 : FE_DRAIN_GROUPS;
-  return h->gemm_nbuf * nfil * FE_GEMM_TILE_M * 4 <= 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M);
+  return h->gemm_nbuf * (nfil + 1) * FE_GEMM_TILE_M * 4 <= 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M);   // (+1: the dummy row)
 }
 
 int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* window, const float* fbank,

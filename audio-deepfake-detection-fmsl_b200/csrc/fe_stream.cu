@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 11);
         {
           float4* z = reinterpret_cast<float4*>(s_E);
-          for (int i = (warp - kMmaWarp0) * 32 + lane; i < nbuf * nfil * kTileM / 4; i += kNumMmaWarps * 32)
+          for (int i = (warp - kMmaWarp0) * 32 + lane; i < nbuf * (nfil + 1) * kTileM / 4; i += kNumMmaWarps * 32)
             z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
@@ -395,8 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       {
         fe_drain_state st;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { st.acc[j] = 0.0f; st.id[j] = -1; }
-        float* e_col = s_E + (cg & (nbuf - 1)) * nfil * kTileM + m;
+        for (int j = 0; j < 4; ++j) { st.acc[j] = 0.0f; st.off[j] = nfil * kTileM; }   // dummy row: no filter yet
+        float* e_col = s_E + (cg & (nbuf - 1)) * (nfil + 1) * kTileM + m;
         const float us2 = s_us2[m];
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int k_begin = cg * cpg;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           }
           tmem_ld_wait();
           tmem_ld_tie8(ce); tmem_ld_tie8(co); tmem_ld_tie8(se); tmem_ld_tie8(so);
-          fe_drain_cols<8>(s_dw + k0, s_dids + k0, ctl, ce, co, se, so, st, e_col, nfil, us2);
+          fe_drain_cols<8>(s_dw + k0, s_dids + k0, ctl, ce, co, se, so, st, e_col, us2);
         }
         if (cg == FE_DRAIN_GROUPS - 1) {
           // bin n_fft/4 from the producers' partial sums (scaled sample units -> accumulator units: x 2^14)
@@ -424,9 +424,9 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           for (int p = 0; p < 4; ++p) { const float2 v = s_midp[p * kTileM + m]; re += v.x; im += v.y; }
           const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
           re *= bs; im *= bs;
-          fe_drain_mid(s_dw + a.nhalf, s_dids + a.nhalf, s_dctl[a.nhalf >> 3], fmaf(re, re, im * im), st, e_col, nfil, us2);
+          fe_drain_mid(s_dw + a.nhalf, s_dids + a.nhalf, s_dctl[a.nhalf >> 3], fmaf(re, re, im * im), st, e_col, us2);
         }
-        fe_drain_flush(st, e_col, nfil, us2);
+        fe_drain_flush(st, e_col, us2);
         if (tid == 0) ST_TRACE(12, it, 0);
       }
       tc_fence_before();
@@ -442,8 +442,9 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         float* dst = a.energies + (size_t)row * nfil * nF + t;
         float vmax = 0.0f;
         for (int f = warp >> 2; f < nfil; f += kWorkerWarps / 4) {   // thread -> frame m, filters f, f+4, ...
-          float v = s_E[f * kTileM + m] + s_E[(nfil + f) * kTileM + m];
-          if (nbuf == 4) v += s_E[(2 * nfil + f) * kTileM + m] + s_E[(3 * nfil + f) * kTileM + m];
+          const int bs = (nfil + 1) * kTileM;   // buffer stride (the last row of each buffer is the dummy row)
+          float v = s_E[f * kTileM + m] + s_E[bs + f * kTileM + m];
+          if (nbuf == 4) v += s_E[2 * bs + f * kTileM + m] + s_E[3 * bs + f * kTileM + m];
           if (valid) {
             dst[(size_t)f * nF] = v;
             vmax = fmaxf(vmax, v);

@@ -151,7 +151,7 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
   const int total = (int)(R * nF), tf = fe_tile_frames(nF);
   const int n_tiles = (total + tf - 1) / tf;
   std::vector<unsigned char> a_stage(fe_gemm_a_stage_bytes());
-  std::vector<float> D((size_t)4 * M * nhalf), E((size_t)4 * FE_GEMM_MAX_FILTERS * M);
+  std::vector<float> D((size_t)4 * M * nhalf), E((size_t)4 * (FE_GEMM_MAX_FILTERS + 1) * M);
   const int nbuf = h->gemm_nbuf;
   std::vector<float> samp, bmax;
   for (int tile = 0; tile < n_tiles; ++tile) {
@@ -221,8 +221,8 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
       const float us2 = unscale[m] * unscale[m];
       for (int cg = 0; cg < FE_DRAIN_GROUPS; ++cg) {
         fe_drain_state st;
-        for (int j = 0; j < 4; ++j) { st.acc[j] = 0.0f; st.id[j] = -1; }
-        float* e_col = E.data() + (size_t)(cg & (nbuf - 1)) * nfil * M + m;
+        for (int j = 0; j < 4; ++j) { st.acc[j] = 0.0f; st.off[j] = nfil * M; }
+        float* e_col = E.data() + (size_t)(cg & (nbuf - 1)) * (nfil + 1) * M + m;
         for (int k0 = cg * cpg; k0 < (cg + 1) * cpg; k0 += 8) {
           float ce[8], co[8], se[8], so[8];
           for (int i = 0; i < 8; ++i) {
@@ -231,22 +231,23 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
             se[i] = D[((size_t)2 * M + m) * nhalf + k0 + i];
             so[i] = D[((size_t)3 * M + m) * nhalf + k0 + i];
           }
-          fe_drain_cols<8>(dw + k0, dids + k0, dctl[k0 >> 3], ce, co, se, so, st, e_col, nfil, us2);
+          fe_drain_cols<8>(dw + k0, dids + k0, dctl[k0 >> 3], ce, co, se, so, st, e_col, us2);
         }
         if (cg == FE_DRAIN_GROUPS - 1) {
           const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
           const float re = mre[m] * bs, im = mim[m] * bs;
-          fe_drain_mid(dw + nhalf, dids + nhalf, dctl[nhalf >> 3], fmaf(re, re, im * im), st, e_col, nfil, us2);
+          fe_drain_mid(dw + nhalf, dids + nhalf, dctl[nhalf >> 3], fmaf(re, re, im * im), st, e_col, us2);
         }
-        fe_drain_flush(st, e_col, nfil, us2);
+        fe_drain_flush(st, e_col, us2);
       }
     }
     // finalize
     for (int m = 0; m < g.count; ++m) {
       const int gi = g.g0 + m, row = gi / nF, t = gi - row * nF;
       for (int f = 0; f < nfil; ++f) {
-        float v = E[(size_t)f * M + m] + E[(size_t)(nfil + f) * M + m];
-        if (nbuf == 4) v += E[(size_t)(2 * nfil + f) * M + m] + E[(size_t)(3 * nfil + f) * M + m];
+        const size_t bs = (size_t)(nfil + 1) * M;
+        float v = E[(size_t)f * M + m] + E[bs + (size_t)f * M + m];
+        if (nbuf == 4) v += E[2 * bs + (size_t)f * M + m] + E[3 * bs + (size_t)f * M + m];
         energies[((size_t)row * nfil + f) * nF + t] = v;
       }
     }
