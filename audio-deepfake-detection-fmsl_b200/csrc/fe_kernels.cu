@@ -463,8 +463,9 @@ static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cuda
   typedef void (*kern_t)(fe_tail_args);
   const int n = a.deltas > 0 ? (a.delta_win - 1) / 2 : 0;
   const bool exact = nc == 4 * kq;
-  const kern_t kern = exact ? (n == 1 ? pick_tail_fast<1, true>(kq) : n == 2 ? pick_tail_fast<2, true>(kq) : pick_tail_fast<0, true>(kq))
-                            : (n == 1 ? pick_tail_fast<1, false>(kq) : n == 2 ? pick_tail_fast<2, false>(kq) : pick_tail_fast<0, false>(kq));
+  // delta half-width 2 (torchaudio's win_length = 5) is unrolled; every other width runs the loop form
+  const kern_t kern = exact ? (n == 2 ? pick_tail_fast<2, true>(kq) : pick_tail_fast<0, true>(kq))
+                            : (n == 2 ? pick_tail_fast<2, false>(kq) : pick_tail_fast<0, false>(kq));
   cudaError_t e = set_smem((const void*)kern, smem);
   if (e != cudaSuccess) return e;
   for (int64_t r0 = 0; r0 < rows; r0 += 65535) {

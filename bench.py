@@ -23,6 +23,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 UTT_LEN = 64600
+NCU_DRAM_BYTES_PER_UTT_STREAM = 287700  # fe_stream_kernel: (307.0 MB read + 33.65 MB written) / 1184 utterances
 SEED = 1234  # the reference's default seed (maze5.py:449)
 
 WORKLOADS = {
@@ -72,7 +73,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._t.start()
@@ -135,11 +136,11 @@ def run_reference_arm(args):
         return 0
     import torch
     w = WORKLOADS[args.workload]
-    per_step_budget = max(1.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step_budget = max(0.25, min(15.0, 100.0 / max(1, args.steps + args.warmup)))   # whole arm: <= ~100 s
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     for _ in range(args.warmup):
-        cpu_reference_throughput(args.workload, min(1.0, per_step_budget), threads=cores)
+        cpu_reference_throughput(args.workload, min(0.5, per_step_budget), threads=cores)
     total_n, total_t, threads = 0, 0.0, cores
     for _ in range(args.steps):
         thr, threads, n = cpu_reference_throughput(args.workload, per_step_budget, threads=cores)
@@ -166,7 +167,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="lfcc", choices=sorted(WORKLOADS))
@@ -280,8 +281,14 @@ def main():
     alg_bytes_step = B * W["bytes_per_utt"]
     dom_gbs = alg_bytes_step / (dom_ms / 1000.0) / 1e9
     step_gbs = alg_bytes_step / (ms_per_step / 1000.0) / 1e9
+    # DRAM traffic of the dominant kernel per launch, from the ncu --set full capture of the same kernel
+    # (profiles/r1_stream_final_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum over 1184 utterances)
+    traffic = None
+    if variant == "dft_gemm" and args.workload == "lfcc":
+        traffic = NCU_DRAM_BYTES_PER_UTT_STREAM * B / max(1, int(dom_launches))
     roofline = {
-        "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+        "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
+        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per utterance x utterances per launch (profiles/r1_stream_final_summary.txt)" if traffic else None,
         "peak_source": peak_src,
         "kernel": ("fe_stream_kernel" if variant == "dft_gemm" else "fe_fft_kernel<1>"),
         "kernel_ms_per_step": dom_ms, "kernel_launches_per_step": int(dom_launches),
