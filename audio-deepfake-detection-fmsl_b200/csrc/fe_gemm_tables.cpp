@@ -102,7 +102,7 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
   }
   // Column groups that share a filter must emit into different buffers.  Two buffers indexed by group parity do
   // when a filter is only ever shared by adjacent groups; otherwise every group gets its own buffer (if the
-  // n_filter x 128 arrays still fit the 32 KB they alias).
+  // n_filter x 128 arrays still fit the 64 KB of A slots they alias).
   bool adjacent_only = true;
   for (int f = 0; f < nfil; ++f) {
     const unsigned m = touched[f];
@@ -111,7 +111,7 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
     if (m != low && m != (low | (low << 1))) adjacent_only = false;
   }
   h->gemm_nbuf = adjacent_only ? 2 : FE_DRAIN_GROUPS;
-  return h->gemm_nbuf * (nfil + 1) * FE_GEMM_TILE_M * 4 <= 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M);   // (+1: the dummy row)
+  return h->gemm_nbuf * (nfil + 1) * FE_GEMM_TILE_M * 4 <= 2 * 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M);   // both A slots (+1: the dummy row)
 }
 
 int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* window, const float* fbank,

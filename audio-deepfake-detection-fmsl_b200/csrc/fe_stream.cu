@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   float* s_gmax = reinterpret_cast<float*>(smem + L.gmax);
   float* s_us2 = reinterpret_cast<float*>(smem + L.us2);
   float2* s_midp = reinterpret_cast<float2*>(smem + L.midp);
-  float* s_E = reinterpret_cast<float*>(smem + L.a_stage);   // drain scratch [nbuf][n_filter][128] aliases A slot 0
+  float* s_E = reinterpret_cast<float*>(smem + L.a_stage);   // drain scratch [nbuf][n_filter + 1][128] aliases the A slots (from slot 0 on)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const uint32_t bars = smem_u32(smem + L.bars);
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };

@@ -319,6 +319,34 @@ def test_dft_gemm_edges_and_short_inputs(fe, T):
     assert_feat_close(b, ref, TOL, f"fft vs torchaudio, T={T}")
 
 
+def test_dft_gemm_other_geometries(fe):
+    """The streaming kernel away from the headline shape: n_fft = 256 with wide filters (a filter spans three
+    column groups -> one emission buffer per group), very short utterances (tiles spanning several of them, tile
+    size below 128 frames), and a mel bank through the sliding-accumulator drain tables."""
+    lib_has = fe._lib.load().b200fe_has_tcgen05()
+    if not lib_has:
+        pytest.skip("tcgen05 variant not built")
+    # (a) n_fft 256, 10 linear filters
+    kw = dict(sample_rate=16000, n_filter=10, n_lfcc=10, speckwargs=dict(n_fft=256, win_length=128, hop_length=64))
+    g, f = fe.LFCC(**kw, variant="dft_gemm"), fe.LFCC(**kw, variant="fft")
+    x = synth.s1_noise(7, 6000, seed=5)
+    ref = O.apply_fbank(O.power_spectrogram(x.astype(np.float64), 256, 128, 64),
+                        O.linear_fbanks(129, 0.0, 8000.0, 10, 16000).astype(np.float64))
+    e = g.engine.fbank_energies(cuda(x)).cpu().numpy()
+    for r in range(x.shape[0]):
+        assert np.abs(e[r] - ref[r]).max() <= 4e-6 * ref[r].max(), r
+    assert_feat_close(g(cuda(x)).cpu().numpy(), f(cuda(x)).cpu().numpy(), TOL, "n_fft=256 dft_gemm vs fft")
+    # (b) 11-frame utterances: a 22-frame tile spans up to three utterances
+    g, f = fe.LFCCDelta(**LFCC_CFG, variant="dft_gemm"), fe.LFCCDelta(**LFCC_CFG, variant="fft")
+    x = synth.s1_noise(37, 1600, seed=6)
+    assert_feat_close(g(cuda(x)).cpu().numpy(), f(cuda(x)).cpu().numpy(), TOL, "T=1600 dft_gemm vs fft")
+    # (c) 24-band mel bank on the LFCC frame geometry
+    mk = dict(sample_rate=16000, n_fft=512, win_length=320, hop_length=160, n_mels=24, log="db")   # wide high bands: one buffer per group
+    g, f = fe.MelSpectrogram(**mk, variant="dft_gemm"), fe.MelSpectrogram(**mk, variant="fft")
+    x = synth.s1_noise(5, 16000, seed=7)
+    assert_feat_close(g(cuda(x)).cpu().numpy(), f(cuda(x)).cpu().numpy(), TOL, "mel dft_gemm vs fft")
+
+
 def test_dft_gemm_amplitude_range(fe):
     """Per-frame fp16 scaling: int16-range and very quiet inputs keep fp32-level relative accuracy."""
     g = _variant_or_skip(fe, "dft_gemm")
