@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(kTailThreads) fe_tail_kernel(fe_tail_args a) {
 // Only the delta stencils go through shared memory.  grid (tiles, rows), block = tt + 2*halo rounded up to a warp.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastMax = 32;
+constexpr int kTailBatch = 10;   // energies fetched per batch (all loads in flight together)
 
 __device__ __forceinline__ float fast_log_energy(float v, int log_mode, float floor_db) {
   if (log_mode == B200FE_LOG_DB) {
@@ -278,16 +279,27 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
     const float* src = a.energies + (size_t)row_local * nfil * nF + (tv0 + tcl);
     if (ncoef > 0) {
       const float4* dr = reinterpret_cast<const float4*>(s_dct);
-#pragma unroll 4
-      for (int f = 0; f < nfil; ++f, src += nF, dr += KQ) {
-        const float v = fast_log_energy(__ldg(src), a.log_mode, floor_db);
+      // the frame's energies come from L2 (~300 cycles): fetch them kTailBatch at a time, all loads in flight together
+#pragma unroll 1
+      for (int f0 = 0; f0 < nfil; f0 += kTailBatch) {
+        float e[kTailBatch];
 #pragma unroll
-        for (int k4 = 0; k4 < KQ; ++k4) {
-          const float4 d = dr[k4];
-          c[4 * k4 + 0] = fmaf(v, d.x, c[4 * k4 + 0]);
-          c[4 * k4 + 1] = fmaf(v, d.y, c[4 * k4 + 1]);
-          c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
-          c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
+        for (int u = 0; u < kTailBatch; ++u) e[u] = (f0 + u < nfil) ? __ldg(src + (size_t)u * nF) : 0.0f;
+        src += (size_t)kTailBatch * nF;
+#pragma unroll
+        for (int u = 0; u < kTailBatch; ++u) {
+          if (f0 + u < nfil) {
+            const float v = fast_log_energy(e[u], a.log_mode, floor_db);
+#pragma unroll
+            for (int k4 = 0; k4 < KQ; ++k4) {
+              const float4 d = dr[k4];
+              c[4 * k4 + 0] = fmaf(v, d.x, c[4 * k4 + 0]);
+              c[4 * k4 + 1] = fmaf(v, d.y, c[4 * k4 + 1]);
+              c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
+              c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
+            }
+          }
+          dr += KQ;
         }
       }
     } else {
