@@ -441,21 +441,36 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         const bool valid = m < g.count;
         float* dst = a.energies + (size_t)row * nfil * nF + t;
         float vmax = 0.0f;
-        for (int f = warp >> 2; f < nfil; f += kWorkerWarps / 4) {   // thread -> frame m, filters f, f+4, ...
-          const int bs = (nfil + 1) * kTileM;   // buffer stride (the last row of each buffer is the dummy row)
-          float v = s_E[f * kTileM + m] + s_E[bs + f * kTileM + m];
-          if (nbuf == 4) v += s_E[2 * bs + f * kTileM + m] + s_E[3 * bs + f * kTileM + m];
-          if (valid) {
-            dst[(size_t)f * nF] = v;
-            vmax = fmaxf(vmax, v);
+        // thread -> frame m, filters f = (warp >> 2) + 4 u: all shared-memory reads first, then the stores
+        const int bsz = (nfil + 1) * kTileM;   // buffer stride (the last row of each buffer is the dummy row)
+        float v[FE_GEMM_MAX_FILTERS / 4];
+#pragma unroll
+        for (int u = 0; u < FE_GEMM_MAX_FILTERS / 4; ++u) {
+          const int f = (warp >> 2) + 4 * u;
+          v[u] = 0.0f;
+          if (f < nfil) {
+            v[u] = s_E[f * kTileM + m] + s_E[bsz + f * kTileM + m];
+            if (nbuf == 4) v[u] += s_E[2 * bsz + f * kTileM + m] + s_E[3 * bsz + f * kTileM + m];
           }
         }
+        if (valid) {
+          float* o = dst + (size_t)(warp >> 2) * nF;
+#pragma unroll
+          for (int u = 0; u < FE_GEMM_MAX_FILTERS / 4; ++u, o += 4 * (size_t)nF) {
+            if ((warp >> 2) + 4 * u < nfil) {
+              *o = v[u];
+              vmax = fmaxf(vmax, v[u]);
+            }
+          }
+        }
+        if (tid == 0) ST_TRACE(13, it, 0);
         if (a.group_max) {
           const int grp_id = (int)((a.row_base + row) / a.top_db_group);
           const int grp0 = __shfl_sync(0xffffffffu, grp_id, 0);
           if (__all_sync(0xffffffffu, grp_id == grp0)) {
-            vmax = warp_max(vmax);
-            if (lane == 0) atomicMax(a.group_max + grp0, __float_as_uint(vmax));
+            // energies are >= 0: the unsigned order of the bit patterns is the float order, one REDUX does the warp
+            const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+            if (lane == 0) atomicMax(a.group_max + grp0, wmax);
           } else if (valid) {
             atomicMax(a.group_max + grp_id, __float_as_uint(vmax));
           }
