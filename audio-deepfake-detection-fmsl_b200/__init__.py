@@ -12,6 +12,7 @@ alias module at the repository root.
 from . import _lib
 from .transforms import (ComputeDeltas, FrontEndEngine, LFCC, LFCCDelta, MelSpectrogram, Spectrogram,
                          create_dct, linear_fbanks, melscale_fbanks)
+from .maze import LFCC_FILTS, FeatureSlot, MazeScorer, fill_deterministic
 from .evaluation import eer_min_dcf, gather_scores, shard_range, write_score_file
 
 # names SURVEY.md 8(b) uses for the drop-in modules
@@ -25,5 +26,6 @@ __all__ = [
     "LFCC", "LFCCDelta", "MelSpectrogram", "Spectrogram", "ComputeDeltas", "FrontEndEngine",
     "B200LFCC", "B200LFCCDelta", "B200MelSpectrogram", "B200Spectrogram", "B200ComputeDeltas",
     "linear_fbanks", "melscale_fbanks", "create_dct",
+    "MazeScorer", "FeatureSlot", "LFCC_FILTS", "fill_deterministic",
     "shard_range", "gather_scores", "eer_min_dcf", "write_score_file",
 ]

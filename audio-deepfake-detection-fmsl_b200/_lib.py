@@ -66,6 +66,7 @@ _SIGNATURES = {
     "b200fe_tables_pack": (C.c_int32, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200fe_tables_variant": (C.c_int32, [_P, C.c_void_p]),
     "b200fe_workspace_bytes": (C.c_int64, [_P, C.c_int64, C.c_int64]),
+    "b200fe_workspace_bytes_ex": (C.c_int64, [_P, C.c_int64, C.c_int64, C.c_int32]),
     "b200fe_spectrogram_forward": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, _P, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200fe_features_forward": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, _P, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -108,13 +108,28 @@ extern "C" int32_t b200fe_resolve_variant(const b200fe_params* p) {
   return (ok && fe_gemm_preferred(p)) ? B200FE_VARIANT_DFT_GEMM : B200FE_VARIANT_FFT;
 }
 
-extern "C" int64_t b200fe_workspace_bytes(const b200fe_params* p, int64_t R, int64_t T) {
+// The streaming tcgen05 kernel fetches dense rows with TMA boxes: ragged clips and pre-emphasised input are
+// first written as dense rows (one chunk at a time) into the workspace.
+static bool needs_dense_rows(const b200fe_params* p, bool ragged) {
+  return p->variant == B200FE_VARIANT_DFT_GEMM && (ragged || p->preemph != 0.0f);
+}
+
+static int64_t dense_rows_bytes(const b200fe_params* p, bool ragged, int64_t chunk, int64_t T) {
+  return needs_dense_rows(p, ragged) ? ((chunk * T * 4 + 255) & ~(int64_t)255) : 0;
+}
+
+extern "C" int64_t b200fe_workspace_bytes_ex(const b200fe_params* p, int64_t R, int64_t T, int32_t ragged) {
   const int64_t nf = b200fe_n_frames(p, T);
   if (nf < 0) return nf;
   if (R < 1) { fe_set_error("R=%lld must be >= 1", (long long)R); return B200FE_ERR_BAD_ARG; }
   if (p->n_filter < 1) { fe_set_error("n_filter must be >= 1 for the feature path"); return B200FE_ERR_BAD_ARG; }
   const int64_t chunk = chunk_rows_for(p, R, nf);
-  return group_max_bytes(p, R) + fe_align16(chunk * p->n_filter * nf * 4) + fe_gemm_workspace_bytes(p, chunk, T);
+  return group_max_bytes(p, R) + ((fe_align16(chunk * p->n_filter * nf * 4) + 255) & ~(int64_t)255) +
+         dense_rows_bytes(p, ragged != 0, chunk, T) + fe_gemm_workspace_bytes(p, chunk, T);
+}
+
+extern "C" int64_t b200fe_workspace_bytes(const b200fe_params* p, int64_t R, int64_t T) {
+  return b200fe_workspace_bytes_ex(p, R, T, 0);
 }
 
 extern "C" int32_t b200fe_spectrogram_forward(const float* wave, int64_t R, int64_t T, const b200fe_params* p,
@@ -165,7 +180,7 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
     return B200FE_ERR_BAD_ARG;
   }
   if (p->n_filter < 1) { fe_set_error("n_filter must be >= 1 for the feature path"); return B200FE_ERR_BAD_ARG; }
-  const int64_t need = b200fe_workspace_bytes(p, R, T);
+  const int64_t need = b200fe_workspace_bytes_ex(p, R, T, offsets != nullptr);
   if (need < 0) return (int32_t)need;
   if (!workspace || workspace_bytes < (size_t)need) {
     fe_set_error("workspace: %zu bytes given, %lld needed", workspace_bytes, (long long)need);
@@ -176,11 +191,11 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
   // a forward call that still says AUTO only sees the device copy and takes the FFT variant.
   int32_t variant = B200FE_VARIANT_FFT;
   if (p->variant == B200FE_VARIANT_DFT_GEMM) {
-    if (!fe_gemm_supported(p) || offsets != nullptr) {
-      fe_set_error("variant dft_gemm does not support this configuration / ragged input");
+    if (!fe_gemm_supported(p)) {
+      fe_set_error("variant dft_gemm does not support this configuration");
       return B200FE_ERR_UNSUPPORTED;
     }
-    if (!fe_stream_supported(p, T, R) || ((uintptr_t)wave & 15) != 0) {
+    if (!fe_stream_supported(p, T, R) || (!needs_dense_rows(p, offsets != nullptr) && ((uintptr_t)wave & 15) != 0)) {
       fe_set_error("variant dft_gemm needs T %% 4 == 0, T > n_fft/2 and a 16-byte aligned waveform (TMA)");
       return B200FE_ERR_UNSUPPORTED;
     }
@@ -193,7 +208,9 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
   const int64_t chunk = chunk_rows_for(p, R, n_frames);
   unsigned int* gmax = needs_group_max(p) ? (unsigned int*)workspace : nullptr;
   float* energies = (float*)((char*)workspace + group_max_bytes(p, R));
-  void* gemm_ws = (char*)energies + fe_align16(chunk * p->n_filter * (int64_t)n_frames * 4);
+  float* dense = (float*)((char*)energies + ((fe_align16(chunk * p->n_filter * (int64_t)n_frames * 4) + 255) & ~(int64_t)255));
+  const bool staged = variant == B200FE_VARIANT_DFT_GEMM && needs_dense_rows(p, offsets != nullptr);
+  void* gemm_ws = (char*)dense + dense_rows_bytes(p, offsets != nullptr, chunk, T);
   const size_t row_energy_floats = (size_t)p->n_filter * n_frames;
 
   if (gmax) {
@@ -252,7 +269,18 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
     if (energies_only) fa.out = out + (size_t)r0 * row_energy_floats;
     if (variant == B200FE_VARIANT_DFT_GEMM) {
       int launches = 0;
-      e = fe_stream_launch(p, fa, r0, nr, gemm_ws, stream, &launches);
+      if (staged) {
+        e = fe_launch_dense_rows(wave, offsets, lengths, r0, nr, T, p->preemph, dense, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "dense-rows kernel launch");
+        g_launches += (nr + 65534) / 65535;
+        fe_fft_args fs = fa;
+        fs.wave = dense - (size_t)r0 * T;  // fe_stream_launch addresses rows absolutely
+        fs.offsets = nullptr;
+        fs.lengths = nullptr;
+        e = fe_stream_launch(p, fs, r0, nr, gemm_ws, stream, &launches);
+      } else {
+        e = fe_stream_launch(p, fa, r0, nr, gemm_ws, stream, &launches);
+      }
       if (e != cudaSuccess) return cuda_fail(e, "dft-gemm kernel launch");
       g_launches += launches;
     } else {

@@ -130,19 +130,24 @@ FE_HD int fe_reflect_index(int pp, int half, int T) {
 // or truncated to T (pad(), Thesis/01_Models/01_Baseline_Models/maze5.py:280-285: sample r =
 // clip[r mod len]); optional pre-emphasis y[r] = x[r] - a*x[r-1], y[0] = x[0]
 // (torchaudio functional/functional.py:2426-2448) is applied before the padding, as torchaudio would.
+// Sample r (0 <= r < T) of the T-sample signal a clip stands for: repeat-pad / truncate, then pre-emphasis.
+FE_HD float fe_padded_sample(const float* src, int clip_len, int T, int r, float preemph) {
+  const bool wrap = clip_len < T;
+  const int c = wrap ? (r % clip_len) : r;
+  float v = src[c];
+  if (preemph != 0.0f && r > 0) {
+    const int c1 = wrap ? ((r - 1) % clip_len) : (r - 1);
+    v = fmaf(-preemph, src[c1], v);
+  }
+  return v;
+}
+
 FE_HD void fe_stage_load(int tid, int nthreads, const float* src, int clip_len, int T, int n_fft, int pp0,
                          int seg, float preemph, float* s_stage) {
   const int half = n_fft >> 1;
-  const bool wrap = clip_len < T;
   for (int i = tid; i < seg; i += nthreads) {
     const int r = fe_reflect_index(pp0 + i, half, T);
-    const int c = wrap ? (r % clip_len) : r;
-    float v = src[c];
-    if (preemph != 0.0f && r > 0) {
-      const int c1 = wrap ? ((r - 1) % clip_len) : (r - 1);
-      v = fmaf(-preemph, src[c1], v);
-    }
-    s_stage[i] = v;
+    s_stage[i] = fe_padded_sample(src, clip_len, T, r, preemph);
   }
 }
 

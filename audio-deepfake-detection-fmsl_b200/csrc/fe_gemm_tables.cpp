@@ -27,7 +27,6 @@ gemm_geom geometry(const b200fe_params* p) {
   const int nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return g;
   if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM
-  if (p->preemph != 0.0f) return g;
   g.ok = true;
   g.kpairs = kpairs;
   g.nhalf = nhalf;

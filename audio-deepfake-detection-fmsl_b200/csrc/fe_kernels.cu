@@ -394,6 +394,43 @@ __global__ void fe_deltas_kernel(const float* __restrict__ in, float* __restrict
   out[row * T + t] = acc / denom;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fe_dense_rows_kernel : clips (ragged, repeat-padded / truncated to T as pad() does, maze5.py:280-285)
+// and / or pre-emphasis -> dense rows [rows][T] the streaming tcgen05 kernel can fetch with TMA boxes.
+// One thread = four consecutive samples of one row (T % 4 == 0), one 16-byte store.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fe_dense_rows_kernel(const float* __restrict__ wave,
+                                                           const int64_t* __restrict__ offsets,
+                                                           const int32_t* __restrict__ lengths, int64_t row_base,
+                                                           int T, float preemph, float* __restrict__ dst) {
+  const int64_t row = row_base + blockIdx.y;
+  const float* src;
+  int clip_len;
+  if (offsets) {
+    src = wave + offsets[row];
+    clip_len = lengths[row];
+  } else {
+    src = wave + row * (int64_t)T;
+    clip_len = T;
+  }
+  float* d = dst + (int64_t)blockIdx.y * T;
+  // same values as fe_padded_sample(), with the clip index carried instead of recomputed per sample
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) * 4; r < T; r += gridDim.x * blockDim.x * 4) {
+    int c = clip_len < T ? r % clip_len : r;
+    float prev = 0.0f;
+    if (preemph != 0.0f && r > 0) prev = src[c == 0 ? clip_len - 1 : c - 1];
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float x = src[c];
+      v[i] = (preemph != 0.0f && r + i > 0) ? fmaf(-preemph, prev, x) : x;
+      prev = x;
+      c = (c + 1 == clip_len && clip_len < T) ? 0 : c + 1;
+    }
+    *reinterpret_cast<float4*>(d + r) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 cudaError_t set_smem(const void* fn, size_t bytes) {
   if (bytes <= 48 * 1024) return cudaSuccess;
   return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -528,6 +565,21 @@ cudaError_t fe_launch_deltas(const float* in, float* out, int64_t rows, int64_t 
     const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
     dim3 grid((unsigned)((T + 255) / 256), (unsigned)nr);
     fe_deltas_kernel<<<grid, 256, 0, stream>>>(in + r0 * T, out + r0 * T, nr, T, n, denom);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t fe_launch_dense_rows(const float* wave, const int64_t* offsets, const int32_t* lengths,
+                                 int64_t row_base, int64_t rows, int64_t T, float preemph, float* dst,
+                                 cudaStream_t stream) {
+  const unsigned bx = (unsigned)((T / 4 + 255) / 256);
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    dim3 grid(bx, (unsigned)nr);
+    fe_dense_rows_kernel<<<grid, 256, 0, stream>>>(wave, offsets, lengths, row_base + r0, (int)T, preemph,
+                                                   dst + r0 * T);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

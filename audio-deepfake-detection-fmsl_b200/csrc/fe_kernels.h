@@ -42,4 +42,9 @@ cudaError_t fe_launch_tail(const fe_tail_args& a, int64_t rows, cudaStream_t str
 cudaError_t fe_launch_cmvn(float* out, int64_t n_series, int n_frames, cudaStream_t stream);
 cudaError_t fe_launch_deltas(const float* in, float* out, int64_t rows, int64_t T, int win,
                              cudaStream_t stream);
+// Dense [rows][T] copy of rows [row_base, row_base+rows): repeat-pad / truncate ragged clips and apply
+// pre-emphasis, so the streaming kernel (TMA boxes over dense rows) serves those inputs too.  T % 4 == 0.
+cudaError_t fe_launch_dense_rows(const float* wave, const int64_t* offsets, const int32_t* lengths,
+                                 int64_t row_base, int64_t rows, int64_t T, float preemph, float* dst,
+                                 cudaStream_t stream);
 #endif

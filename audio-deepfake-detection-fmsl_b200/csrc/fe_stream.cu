@@ -515,7 +515,6 @@ bool fe_gemm_supported(const b200fe_params* p) {
   const int kpairs = p->win_length / 2, nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return false;
   if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return false;   // 4 accumulators fit TMEM
-  if (p->preemph != 0.0f) return false;
   return make_layout(p->hop_length, nhalf, kpairs).total <= 227 * 1024;
 }
 

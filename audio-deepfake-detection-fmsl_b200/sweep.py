@@ -1,0 +1,91 @@
+"""Evaluation sweep of BASELINE config 4: an ASVspoof2019-LA-eval-sized set (71,237 utterances: 7,355
+bonafide + 63,882 spoofed, Thesis/02_Evaluation_Scripts/Eval.py:58-60) of synthetic 4 s utterances, sharded
+over the ranks, front-end -> maze5 classifier -> bonafide score per utterance (maze5.py:415-430), ONE
+all_gather of the scores (NCCL over NVLink), EER / min-DCF on rank 0 as Maze5_eval.py:588-594 computes them.
+
+Mirrors ``produce_evaluation_file`` (Maze5_eval.py:412-508) without its per-batch device->host sync and
+text-file round trip: scores stay on the device until the gather.  The utterance with global index ``g`` is
+the same whatever the world size (it is drawn from a generator seeded by its block of 1024 utterances), so
+the score vector, and with it the EER, must not depend on how the sweep is sharded.
+"""
+from __future__ import annotations
+
+import hashlib
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+from .evaluation import eer_min_dcf, gather_scores, shard_range
+
+N_BONAFIDE, N_SPOOF = 7355, 63882          # Eval.py:58-60
+N_EVAL = N_BONAFIDE + N_SPOOF              # 71,237
+UTT_LEN = 64600
+BLOCK = 1024                               # utterances drawn per generator seed
+SEED = 1234                                # the reference's seed (maze5.py:449)
+
+
+def synthetic_block(block: int, device: torch.device, n_total: int = N_EVAL, n_bonafide: int = N_BONAFIDE,
+                    seed: int = SEED) -> Tensor:
+    """Utterances ``[block*1024, min(n_total, (block+1)*1024))`` as ``(n,64600)`` float32 on ``device``:
+    set S1 (``0.1*N(0,1)`` clipped to [-1,1]); bonafide utterances (the first ``n_bonafide``) at half the
+    amplitude so that the two classes are separable by a score and the EER is not a coin flip."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 7919 * block)
+    lo = block * BLOCK
+    n = min(n_total, lo + BLOCK) - lo
+    x = torch.randn((BLOCK, UTT_LEN), generator=g, device=device, dtype=torch.float32)[:n]
+    x = (0.1 * x).clamp_(-1.0, 1.0)
+    idx = torch.arange(lo, lo + n, device=device)
+    return x * torch.where(idx < n_bonafide, 0.5, 1.0).unsqueeze(1)
+
+
+def labels(n_total: int = N_EVAL, n_bonafide: int = N_BONAFIDE) -> np.ndarray:
+    """1 = bonafide, 0 = spoof (Maze5_eval.py:556-566)."""
+    return (np.arange(n_total) < n_bonafide).astype(np.int64)
+
+
+def run_sweep(frontend: nn.Module, scorer: nn.Module, device: torch.device, *, n_total: int = N_EVAL,
+              n_bonafide: int = N_BONAFIDE, batch: int = BLOCK, rank: int = 0, world_size: int = 1,
+              group: Optional[dist.ProcessGroup] = None) -> Dict[str, object]:
+    """Score this rank's shard, gather, and (every rank) return the metrics.  ``frontend`` maps ``(B,T)`` to
+    ``(B,C,n_frames)``; ``scorer`` maps those features to ``(B,2)`` log-softmax.  Times are device times
+    (CUDA events) of the front-end alone and of front-end + classifier, plus the wall time of the whole sweep."""
+    if batch < 1 or BLOCK % batch != 0:
+        raise ValueError(f"batch must divide {BLOCK}")
+    lo, hi = shard_range(n_total, rank, world_size)
+    local = torch.empty(hi - lo, dtype=torch.float32, device=device)
+    fe_ms = cls_ms = 0.0
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    timed = []
+    for block in range(lo // BLOCK, (max(hi, 1) - 1) // BLOCK + 1 if hi > lo else 0):
+        xb = synthetic_block(block, device, n_total, n_bonafide)
+        b_lo = block * BLOCK
+        s, e = max(lo, b_lo) - b_lo, min(hi, b_lo + xb.shape[0]) - b_lo
+        for i in range(s, e, batch):
+            x = xb[i:min(e, i + batch)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            feats = frontend(x)
+            ev[1].record()
+            with torch.no_grad():
+                out = scorer(feats)
+            ev[2].record()
+            local[b_lo + i - lo: b_lo + i - lo + x.shape[0]] = out[:, 1]       # maze5.py:425
+            timed.append(ev)
+    torch.cuda.synchronize(device)
+    for a, b, c in timed:
+        fe_ms += a.elapsed_time(b)
+        cls_ms += b.elapsed_time(c)
+    full = gather_scores(local, n_total, group)
+    scores = full.cpu().numpy()
+    wall = time.perf_counter() - t0
+    eer, dcf, thr = eer_min_dcf(labels(n_total, n_bonafide), scores)
+    return dict(n_total=n_total, n_local=hi - lo, eer=eer, min_dcf=dcf, eer_threshold=thr,
+                scores_sha256=hashlib.sha256(scores.astype("<f4").tobytes()).hexdigest(),
+                frontend_ms=fe_ms, classifier_ms=cls_ms, wall_s=wall, scores=scores)

@@ -235,15 +235,16 @@ class FrontEndEngine:
             if offsets.device != dev or lengths.device != dev:
                 raise ValueError("offsets / lengths must be on the waveform's device")
         p = self._params_with_group(group)
-        if offsets is not None and self.requested_variant == "auto" and p.variant != _lib.VARIANT_FFT:
-            # ragged (repeat-pad) input is implemented by the FFT variant only; AUTO may switch, an explicit
+        if (p.variant == _lib.VARIANT_DFT_GEMM and self.requested_variant == "auto"
+                and (T % 4 != 0 or (offsets is None and p.preemph == 0.0 and wave2d.data_ptr() % 16 != 0))):
+            # the streaming kernel's TMA boxes need 16-byte aligned rows; AUTO may switch, an explicit
             # variant request may not (the library then reports "unsupported")
             p = _lib.Params.from_buffer_copy(p)
             p.variant = _lib.VARIANT_FFT
         nf = self.n_frames(T)
         if out is None:
             out = torch.empty((R, self.n_out, nf), dtype=torch.float32, device=dev)
-        ws_bytes = _lib.check(self.lib.b200fe_workspace_bytes(C.byref(p), R, T))
+        ws_bytes = _lib.check(self.lib.b200fe_workspace_bytes_ex(C.byref(p), R, T, 0 if offsets is None else 1))
         ws = self.workspace_on(dev, ws_bytes)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream

@@ -117,6 +117,10 @@ int32_t b200fe_tables_variant(const b200fe_params* p, const void* blob_host);
 /* Scratch needed by b200fe_features_forward for R rows of T samples (filterbank energies of one
  * chunk of rows + per-group maxima).  <0 on bad args. */
 int64_t b200fe_workspace_bytes(const b200fe_params* p, int64_t R, int64_t T);
+/* The same for a call that passes offsets / lengths (ragged != 0): with params.variant ==
+ * B200FE_VARIANT_DFT_GEMM ragged clips (and pre-emphasised input, ragged or not) are first written as
+ * dense repeat-padded rows, one chunk of rows at a time, into the workspace, which grows by chunk*T*4 bytes. */
+int64_t b200fe_workspace_bytes_ex(const b200fe_params* p, int64_t R, int64_t T, int32_t ragged);
 
 /* Replaces Spectrogram.forward (transforms/_transforms.py:25; functional.py:119-145, power=2):
  *   wave  float32 device [R][T] contiguous           out  float32 device [R][n_fft/2+1][n_frames]   */
@@ -131,7 +135,7 @@ int32_t b200fe_spectrogram_forward(const float* wave, int64_t R, int64_t T, cons
  *            (sample i = clip[i mod len]; clips longer than T keep their first T samples).
  *   offsets  int64 device [R] or NULL;   lengths  int32 device [R] or NULL (both or neither)
  *   out      float32 device [R][n_out_channels][n_frames] contiguous
- *   workspace  device scratch of at least b200fe_workspace_bytes(p,R,T), 16-byte aligned           */
+ *   workspace  device scratch of at least b200fe_workspace_bytes_ex(p,R,T,offsets != NULL), 16-byte aligned */
 int32_t b200fe_features_forward(const float* wave, int64_t R, int64_t T, const int64_t* offsets,
                                 const int32_t* lengths, const b200fe_params* p, const void* tables,
                                 float* out, void* workspace, size_t workspace_bytes, void* stream);

@@ -29,7 +29,6 @@ def test_gemm_tables_available_for_lfcc_config(fe):
     dict(speckwargs=dict(n_fft=1024, win_length=1024, hop_length=512)),        # n_fft/4 > 128 columns
     dict(speckwargs=dict(n_fft=512, win_length=320, hop_length=160, window_fn=__import__("torch").hamming_window)),
     dict(speckwargs=dict(n_fft=512, win_length=320, hop_length=160), n_filter=128),
-    dict(speckwargs=dict(n_fft=512, win_length=320, hop_length=160), preemphasis=0.97),
 ])
 def test_gemm_unsupported_configs_fall_to_fft_or_raise(fe, kw):
     base = dict(sample_rate=16000, n_filter=20, n_lfcc=20)
@@ -39,6 +38,12 @@ def test_gemm_unsupported_configs_fall_to_fft_or_raise(fe, kw):
         fe.LFCC(**base, variant="dft_gemm")                           # explicit request: no silent fallback
     with pytest.raises(NotImplementedError):
         fe.MelSpectrogram(**MEL_CFG, variant="dft_gemm")
+
+
+def test_preemphasis_keeps_the_tensor_core_variant(fe):
+    # pre-emphasised (and ragged) input reaches the streaming kernel as dense rows (fe_dense_rows_kernel)
+    m = fe.LFCC(16000, n_filter=20, n_lfcc=20, speckwargs=dict(n_fft=512, win_length=320, hop_length=160), preemphasis=0.97)
+    assert m.engine.resolved_variant() == "dft_gemm"
 
 
 def test_emulated_gemm_energies_lfcc(fe):

@@ -197,16 +197,41 @@ def test_ragged_repeat_pad(fe):
     flat, offsets, lengths = synth.s4_ragged(24)
     lengths[0], lengths[1] = 64600, 64601
     dense = np.stack([O.pad_repeat(flat[o:o + l], 64600) for o, l in zip(offsets, lengths)])
-    m = fe.LFCCDelta(**LFCC_CFG, variant="fft")   # the repeat-pad loader lives in the FFT variant
-    a = m.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600)
-    b = m(cuda(dense))
-    assert a.shape == (24, 60, 404)
-    assert torch.equal(a, b)
-    # AUTO switches to the FFT variant for ragged input instead of failing
-    auto = fe.LFCCDelta(**LFCC_CFG)
-    assert torch.equal(auto.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600), a)
     ref = LFCCDeltaRef()(torch.from_numpy(dense)).numpy()
-    assert_feat_close(a.cpu().numpy(), ref, TOL, "ragged vs torchaudio on pad()-ed clips")
+    # FFT variant: repeat-pad inside the loader.  Tensor-core variant (what AUTO takes): clips are written as
+    # dense repeat-padded rows by fe_dense_rows_kernel, then the streaming kernel runs on those rows.
+    for variant in ("fft", "auto"):
+        m = fe.LFCCDelta(**LFCC_CFG, variant=variant)
+        a = m.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600)
+        b = m(cuda(dense))
+        assert a.shape == (24, 60, 404)
+        assert torch.equal(a, b), variant     # ragged call == dense call on the pad()-ed clips, bit for bit
+        assert_feat_close(a.cpu().numpy(), ref, TOL, f"ragged ({variant}) vs torchaudio on pad()-ed clips")
+
+
+def test_preemphasis_both_variants(fe):
+    """Pre-emphasis (torchaudio functional.py:2426) ahead of the LFCC path, applied before the reflect padding."""
+    x = synth.s1_noise(6)
+    ref = LFCCDeltaRef(preemph=0.97)(torch.from_numpy(x)).numpy()
+    for variant in ("fft", "auto"):
+        m = fe.LFCCDelta(**LFCC_CFG, variant=variant, preemphasis=0.97)
+        assert_feat_close(m(cuda(x)).cpu().numpy(), ref, TOL, f"pre-emphasis ({variant})")
+    flat, offsets, lengths = synth.s4_ragged(5)
+    dense = np.stack([O.pad_repeat(flat[o:o + l], 64600) for o, l in zip(offsets, lengths)])
+    m = fe.LFCCDelta(**LFCC_CFG, preemphasis=0.97)
+    assert torch.equal(m.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600), m(cuda(dense)))
+
+
+def test_auto_falls_back_for_rows_tma_cannot_fetch(fe):
+    """T % 4 != 0 or a misaligned view: AUTO takes the FFT variant, an explicit dft_gemm request raises."""
+    x = synth.s1_noise(3, 64602)
+    ref = LFCCDeltaRef()(torch.from_numpy(x)).numpy()
+    assert_feat_close(fe.LFCCDelta(**LFCC_CFG)(cuda(x)).cpu().numpy(), ref, TOL, "T % 4 != 0")
+    with pytest.raises(NotImplementedError):
+        fe.LFCCDelta(**LFCC_CFG, variant="dft_gemm")(cuda(x))
+    y = cuda(synth.s1_noise(1, 3 * 64600 + 1)).reshape(-1)[1:].reshape(3, 64600)   # rows 4 bytes off 16-byte alignment
+    ref = LFCCDeltaRef()(y.cpu()).numpy()
+    assert_feat_close(fe.LFCCDelta(**LFCC_CFG)(y).cpu().numpy(), ref, TOL, "misaligned view")
 
 
 def test_cmvn_extension(fe):
@@ -373,10 +398,8 @@ def test_auto_variant_and_explicit_errors(fe):
     assert fe.MelSpectrogram(**MEL_CFG, log="db").engine.resolved_variant() == "fft"
     with pytest.raises(NotImplementedError):
         fe.MelSpectrogram(**MEL_CFG, variant="dft_gemm")
-    m = fe.LFCCDelta(**LFCC_CFG, variant="dft_gemm")
-    flat, offsets, lengths = synth.s4_ragged(4)
-    with pytest.raises(NotImplementedError):   # ragged input is an FFT-variant feature: no silent switch
-        m.forward_ragged(cuda(flat), cuda(offsets), cuda(lengths), 64600)
+    with pytest.raises(NotImplementedError):
+        fe.LFCCDelta(**{**LFCC_CFG, "speckwargs": dict(n_fft=512, win_length=400, hop_length=160)}, variant="dft_gemm")
 
 
 def test_fast_tail_equals_generic_tail(fe, monkeypatch):
