@@ -54,13 +54,6 @@ int64_t chunk_rows_for(const b200fe_params* p, int64_t R, int64_t n_frames) {
   return c < R ? c : R;
 }
 
-int pick_ft(const b200fe_params* p, int n_ch) {
-  for (int ft = 32; ft >= 4; ft >>= 1) {
-    if (fe_fft_smem_bytes(p->n_fft, p->hop_length, ft, n_ch) <= 200 * 1024) return ft;
-  }
-  return 0;
-}
-
 int pick_tt(int n_frames) {
   const int tiles = (n_frames + 127) / 128;
   int tt = (n_frames + tiles - 1) / tiles;
@@ -138,7 +131,7 @@ extern "C" int32_t b200fe_spectrogram_forward(const float* wave, int64_t R, int6
   int32_t st = common_checks(p, wave, R, T, tables, out);
   if (st != B200FE_OK) return st;
   const int n_freq = p->n_fft / 2 + 1;
-  const int ft = pick_ft(p, n_freq);
+  const int ft = fe_fft_pick_ft(p->n_fft, p->hop_length, n_freq, 0);
   if (ft == 0) { fe_set_error("n_fft=%d hop=%d does not fit shared memory", p->n_fft, p->hop_length); return B200FE_ERR_UNSUPPORTED; }
   fe_fft_args a;
   memset(&a, 0, sizeof(a));
@@ -235,7 +228,7 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
   fa.top_db_group = p->top_db_group;
   fa.preemph = p->preemph;
   if (variant == B200FE_VARIANT_FFT) {
-    fa.ft = pick_ft(p, p->n_filter);
+    fa.ft = fe_fft_pick_ft(p->n_fft, p->hop_length, p->n_filter, 1);
     if (fa.ft == 0) { fe_set_error("n_fft=%d hop=%d does not fit shared memory", p->n_fft, p->hop_length); return B200FE_ERR_UNSUPPORTED; }
     fa.tiles_per_row = (n_frames + fa.ft - 1) / fa.ft;
   }

@@ -145,6 +145,7 @@ FE_HD float fe_padded_sample(const float* src, int clip_len, int T, int r, float
 FE_HD void fe_stage_load(int tid, int nthreads, const float* src, int clip_len, int T, int n_fft, int pp0,
                          int seg, float preemph, float* s_stage) {
   const int half = n_fft >> 1;
+#pragma unroll 4
   for (int i = tid; i < seg; i += nthreads) {
     const int r = fe_reflect_index(pp0 + i, half, T);
     s_stage[i] = fe_padded_sample(src, clip_len, T, r, preemph);

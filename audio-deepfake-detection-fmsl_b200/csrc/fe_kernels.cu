@@ -6,6 +6,7 @@
 //   fe_deltas_kernel stand-alone ComputeDeltas
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "fe_fft.cuh"
 #include "fe_tail.cuh"
@@ -20,6 +21,128 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Register-resident warp FFT (the fast path of fe_fft_kernel for n_fft = 64*E, E in {4, 8, 16}).
+// One warp = one frame; the n_fft/2-point complex transform of the packed sequence is factored as
+// N = E x 32 with n = lane + 32*j:  (1) an E-point DFT over j in each lane's registers,  (2) the twiddle
+// W_N^(lane*k2),  (3) a 32-point DFT over the lanes with five butterfly-exchange stages.  Both DFTs are
+// radix-2 decimation-in-frequency, so register i of lane l ends up holding  Z[E*bitrev5(l) + bitrevE(i)].
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr float fe_cos16(int k) {  // cos(2*pi*k/16)
+  constexpr float c1 = 0.92387953251128674f, c2 = 0.70710678118654752f, c3 = 0.38268343236508977f;
+  switch (k & 15) {
+    case 0: return 1.0f;
+    case 1: case 15: return c1;
+    case 2: case 14: return c2;
+    case 3: case 13: return c3;
+    case 4: case 12: return 0.0f;
+    case 5: case 11: return -c3;
+    case 6: case 10: return -c2;
+    case 7: case 9: return -c1;
+    default: return -1.0f;
+  }
+}
+__host__ __device__ constexpr float fe_sin16(int k) { return fe_cos16(k + 12); }  // sin(x) = cos(x - pi/2)
+__host__ __device__ constexpr int fe_ilog2(int e) { return e <= 1 ? 0 : 1 + fe_ilog2(e >> 1); }
+__host__ __device__ constexpr int fe_bitrev(int i, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; ++b) r = (r << 1) | ((i >> b) & 1);
+  return r;
+}
+
+template <int E>
+__device__ __forceinline__ void fe_regs_dft(float2 (&v)[E]) {
+#pragma unroll
+  for (int half = E / 2; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int base = 0; base < E; base += 2 * half) {
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float2 a = v[base + i], b = v[base + i + half];
+        v[base + i] = make_float2(a.x + b.x, a.y + b.y);
+        const float dx = a.x - b.x, dy = a.y - b.y;
+        const int k16 = i * (8 / half);  // W_(2*half)^i = exp(-2*pi*i*k16/16)
+        if (k16 == 0) {
+          v[base + i + half] = make_float2(dx, dy);
+        } else if (k16 == 4) {
+          v[base + i + half] = make_float2(dy, -dx);
+        } else {
+          const float c = fe_cos16(k16), sn = fe_sin16(k16);
+          v[base + i + half] = make_float2(fmaf(dy, sn, dx * c), fmaf(-dx, sn, dy * c));
+        }
+      }
+    }
+  }
+}
+
+// Index of Z[k] (8-byte units) in the per-warp buffer: padded so that the scattered store after the lane
+// exchange (k = E*bitrev5(lane) + k2) and the sequential loads of the split phase are both conflict-free.
+template <int E>
+__device__ __forceinline__ int fe_zunit(int k) {
+  constexpr int L = fe_ilog2(E);
+  return k + (k >> L) + (k >> (L + 4));
+}
+
+template <int E>
+__device__ __forceinline__ void fe_warp_rfft_power(int lane, const float* __restrict__ frame,
+                                                   const float* __restrict__ s_win, const float2 (&tw2)[E],
+                                                   const float2 (&twx)[4], const fe_c2* __restrict__ s_rtw,
+                                                   float2* zbuf, float* pw, int pw_stride) {
+  constexpr int NH = 32 * E;
+  float2 v[E];
+  const float2* f2 = reinterpret_cast<const float2*>(frame);
+  const float2* w2 = reinterpret_cast<const float2*>(s_win);
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const float2 x = f2[lane + 32 * j], w = w2[lane + 32 * j];
+    v[j] = make_float2(x.x * w.x, x.y * w.y);
+  }
+  fe_regs_dft<E>(v);
+#pragma unroll
+  for (int i = 1; i < E; ++i) {   // register 0 is k2 = 0: twiddle 1
+    const float2 t = tw2[i], a = v[i];
+    v[i] = make_float2(fmaf(-a.y, t.y, a.x * t.x), fmaf(a.x, t.y, a.y * t.x));
+  }
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int half = 16 >> s;
+    const float sgn = (lane & half) ? -1.0f : 1.0f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float px = __shfl_xor_sync(0xffffffffu, v[i].x, half);
+      const float py = __shfl_xor_sync(0xffffffffu, v[i].y, half);
+      const float tx = fmaf(sgn, v[i].x, px), ty = fmaf(sgn, v[i].y, py);   // upper: v + p, lower: p - v
+      if (s < 4) {
+        const float2 t = twx[s];                                             // upper lanes hold (1, 0)
+        v[i] = make_float2(fmaf(-ty, t.y, tx * t.x), fmaf(tx, t.y, ty * t.x));
+      } else {
+        v[i] = make_float2(tx, ty);
+      }
+    }
+  }
+  const int kbase = E * (int)(__brev((unsigned)lane) >> 27);
+#pragma unroll
+  for (int i = 0; i < E; ++i) zbuf[fe_zunit<E>(kbase + fe_bitrev(i, fe_ilog2(E)))] = v[i];
+  __syncwarp();
+  // real-FFT split + power (the arithmetic of fe_fft_power, padded Z addressing); bin k of this frame goes to
+  // pw[k * pw_stride] (the CTA's [bin][frame] tile).  Lane l takes k = l + 32*i, i < NH/64, lane 0 also k = NH/2.
+#pragma unroll
+  for (int i = 0; i <= NH / 64; ++i) {
+    const int k = lane + 32 * i;
+    if (i == NH / 64 && lane != 0) break;
+    const float2 a = zbuf[fe_zunit<E>(k)];
+    const float2 b = zbuf[fe_zunit<E>((NH - k) & (NH - 1))];
+    const float ex = a.x + b.x, ey = a.y - b.y;   // 2*Fe
+    const float ox = a.y + b.y, oy = b.x - a.x;   // 2*Fo
+    const fe_c2 r = s_rtw[k];
+    const float tx = r.x * ox - r.y * oy, ty = r.x * oy + r.y * ox;
+    const float px = ex + tx, py = ey + ty, mx = ex - tx, my = ey - ty;
+    pw[(size_t)k * pw_stride] = 0.25f * (px * px + py * py);
+    pw[(size_t)(NH - k) * pw_stride] = 0.25f * (mx * mx + my * my);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -145,6 +268,142 @@ __global__ void __launch_bounds__(kFftThreads) fe_fft_kernel(fe_fft_args a) {
 #pragma unroll
       for (int w = 1; w < kFftWarps; ++w) m = fmaxf(m, s_red[w]);
       // energies are >= 0, so the unsigned ordering of the bit patterns is the float ordering
+      atomicMax(a.group_max + row / a.top_db_group, __float_as_uint(m));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fe_rfft_kernel : the FFT variant's fast path (n_fft = 64*E, even hop).  Same grid, arguments and results
+// as fe_fft_kernel; differences: register-resident warp FFT, powers of the CTA's frames collected in one
+// transposed [bin][frame] tile, and the filterbank applied by the whole CTA afterwards with
+// lane = frame (every warp walks a band of warp-uniform length: no imbalance between narrow and wide filters).
+//   FT = frames per CTA (16 or 32): a warp covers 32/FT filters x FT frames per step of the filterbank phase.
+// ------------------------------------------------------------------------------------------------
+template <int E>
+__host__ __device__ constexpr int fe_rfft_zunits() { return 32 * E - 1 + ((32 * E - 1) >> fe_ilog2(E)) + ((32 * E - 1) >> (fe_ilog2(E) + 4)) + 1; }
+
+template <int MODE, int E>
+__global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NH = 32 * E, NFFT = 2 * NH, NFREQ = NH + 1;
+  const int hop = a.hop, ft = a.ft, stride = ft + 1;
+  const int seg = (ft - 1) * hop + NFFT;
+
+  float* s_stage = reinterpret_cast<float*>(smem_raw);
+  size_t off = ((size_t)seg * 4 + 15) & ~(size_t)15;
+  float* s_win = reinterpret_cast<float*>(smem_raw + off);
+  off += (size_t)NFFT * 4;
+  fe_c2* s_rtw = reinterpret_cast<fe_c2*>(smem_raw + off);
+  off += (((size_t)(NH / 2 + 1) * 8) + 15) & ~(size_t)15;
+  float2* s_z = reinterpret_cast<float2*>(smem_raw + off);   // [warps][zunits]
+  off += (size_t)kFftWarps * fe_rfft_zunits<E>() * 8;
+  float* s_pw = reinterpret_cast<float*>(smem_raw + off);    // [NFREQ][ft+1]
+  off += (((size_t)NFREQ * stride * 4) + 15) & ~(size_t)15;
+  float* s_tile = reinterpret_cast<float*>(smem_raw + off);  // MODE 1: [n_filter][ft+1]
+  off += (MODE == 1) ? ((((size_t)a.n_filter * stride * 4) + 15) & ~(size_t)15) : 0;
+  float* s_bw = reinterpret_cast<float*>(smem_raw + off);    // MODE 1: band weights
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row_local = blockIdx.x / a.tiles_per_row;
+  const int tile = blockIdx.x - (int)(row_local * a.tiles_per_row);
+  const int64_t row = a.row_base + row_local;
+  const int t0 = tile * ft;
+  const int nf_here = min(ft, a.n_frames - t0);
+
+  const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
+  const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
+  const fe_c2* gt = reinterpret_cast<const fe_c2*>(blob + h->off_twiddle);
+
+  // ---- constants -> shared, frame-independent twiddles -> registers ------------------------------
+  {
+    const float4* gw = reinterpret_cast<const float4*>(blob + h->off_window);
+    for (int i = tid; i < NFFT / 4; i += kFftThreads) reinterpret_cast<float4*>(s_win)[i] = gw[i];
+    const fe_c2* gr = reinterpret_cast<const fe_c2*>(blob + h->off_rtwiddle);
+    for (int i = tid; i <= NH / 2; i += kFftThreads) s_rtw[i] = gr[i];
+  }
+  const float* bwp = reinterpret_cast<const float*>(blob + h->off_band_w);
+  if (MODE == 1 && h->total_w <= 2 * NFREQ + 2 * a.n_filter) {   // fe_rfft_bw_cap: weights fit the shared copy
+    for (int i = tid; i < h->total_w; i += kFftThreads) s_bw[i] = bwp[i];
+    bwp = s_bw;
+  }
+  float2 tw2[E], twx[4];
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const fe_c2 t = gt[lane * fe_bitrev(i, fe_ilog2(E))];             // W_NH^(lane * k2)
+    tw2[i] = make_float2(t.x, t.y);
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int half = 16 >> s;
+    const fe_c2 t = gt[(lane & (half - 1)) * (16 / half) * E];         // W_(2*half)^(lane mod half)
+    twx[s] = (lane & half) ? make_float2(t.x, t.y) : make_float2(1.0f, 0.0f);
+  }
+
+  // ---- stage the waveform segment (as fe_fft_kernel) ----------------------------------------------
+  {
+    const float* src;
+    int clip_len;
+    if (a.offsets) {
+      src = a.wave + a.offsets[row];
+      clip_len = a.lengths[row];
+    } else {
+      src = a.wave + row * a.T;
+      clip_len = (int)a.T;
+    }
+    const int seg_here = (nf_here - 1) * hop + NFFT;
+    fe_stage_load(tid, kFftThreads, src, clip_len, (int)a.T, NFFT, t0 * hop, seg_here, a.preemph, s_stage);
+  }
+  __syncthreads();
+
+  // ---- one warp = one frame: FFT in registers, powers into the [bin][frame] tile -------------------
+  float2* zbuf = s_z + (size_t)warp * fe_rfft_zunits<E>();
+  for (int fl = warp; fl < nf_here; fl += kFftWarps) {
+    fe_warp_rfft_power<E>(lane, s_stage + (size_t)fl * hop, s_win, tw2, twx, s_rtw, zbuf, s_pw + fl, stride);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- filterbank: lane -> (filter slot, frame); the band loop has the same length for a whole warp step ----
+  const float* tile_src = s_pw;
+  int n_ch = NFREQ;
+  const int tl = lane & (ft - 1), sub = lane / ft, fpw = 32 / ft;     // ft is 16 or 32
+  if (MODE == 1) {
+    const int32_t* bstart = reinterpret_cast<const int32_t*>(blob + h->off_band_start);
+    const int32_t* blen = reinterpret_cast<const int32_t*>(blob + h->off_band_len);
+    const int32_t* bwoff = reinterpret_cast<const int32_t*>(blob + h->off_band_woff);
+    for (int f = warp * fpw + sub; f < a.n_filter; f += kFftWarps * fpw) {
+      const int s0 = bstart[f], len = blen[f];
+      const float* w = bwp + bwoff[f];
+      const float* pcol = s_pw + (size_t)s0 * stride + tl;
+      float acc = 0.0f;                                               // same summation order as fe_fbank_apply
+      for (int i = 0; i < len; ++i) acc = fmaf(pcol[(size_t)i * stride], w[i], acc);
+      s_tile[(size_t)f * stride + tl] = acc;
+    }
+    __syncthreads();
+    tile_src = s_tile;
+    n_ch = a.n_filter;
+  }
+
+  // ---- coalesced tile store (+ group maximum) --------------------------------------------------
+  float* dst = a.out + ((size_t)row_local * n_ch) * a.n_frames + t0;
+  float vmax = 0.0f;
+  if (tl < nf_here) {
+    for (int c = warp * fpw + sub; c < n_ch; c += kFftWarps * fpw) {
+      const float v = tile_src[(size_t)c * stride + tl];
+      dst[(size_t)c * a.n_frames + tl] = v;
+      vmax = fmaxf(vmax, v);
+    }
+  }
+  if (MODE == 1 && a.group_max) {
+    vmax = warp_max(vmax);
+    __shared__ float s_red[kFftWarps];
+    if (lane == 0) s_red[warp] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+      float m = s_red[0];
+#pragma unroll
+      for (int w = 1; w < kFftWarps; ++w) m = fmaxf(m, s_red[w]);
       atomicMax(a.group_max + row / a.top_db_group, __float_as_uint(m));
     }
   }
@@ -444,33 +703,71 @@ int fe_fft_warps_for(int n_fft) {
   return w > kFftWarps ? kFftWarps : (w < 1 ? 1 : w);
 }
 
-size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch) {
+int fe_fft_fast_e(int n_fft, int hop) {
+  // register-resident warp FFT where the geometry allows it (B200FE_SMEM_FFT: test hook for the Stockham path)
+  if ((hop & 1) != 0 || getenv("B200FE_SMEM_FFT") != nullptr) return 0;
+  return n_fft == 256 ? 4 : n_fft == 512 ? 8 : n_fft == 1024 ? 16 : 0;
+}
+
+// Band weights are copied to shared memory when they fit this many floats (any triangular bank does).
+static int fe_rfft_bw_cap(int n_fft, int n_filter) { return 2 * (n_fft / 2 + 1) + 2 * n_filter; }
+
+size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch, int mode) {
   const int nh = n_fft / 2;
   size_t seg = (size_t)(ft - 1) * hop + n_fft;
   size_t b = (seg * 4 + 15) & ~(size_t)15;
+  const int E = fe_fft_fast_e(n_fft, hop);
+  if (E > 0) {
+    const int zunits = E == 4 ? fe_rfft_zunits<4>() : E == 8 ? fe_rfft_zunits<8>() : fe_rfft_zunits<16>();
+    b += (size_t)n_fft * 4 + ((((size_t)(nh / 2 + 1)) * 8 + 15) & ~(size_t)15);
+    b += (size_t)kFftWarps * zunits * 8;
+    b += (((size_t)(nh + 1) * (ft + 1) * 4) + 15) & ~(size_t)15;
+    if (mode == 1) b += ((((size_t)n_ch * (ft + 1) * 4) + 15) & ~(size_t)15) + (size_t)fe_rfft_bw_cap(n_fft, n_ch) * 4;
+    return b;
+  }
   b += (size_t)n_fft * 4 + (size_t)nh * 8 + ((((size_t)(nh / 2 + 1)) * 8 + 15) & ~(size_t)15);
   b += (size_t)fe_fft_warps_for(n_fft) * 2 * (nh + 1) * 8;
   b += (size_t)n_ch * (ft + 1) * 4;
   return b;
 }
 
+// Frames per CTA: the fast path wants several CTAs per SM (phases of different CTAs overlap) and 16 or 32
+// frames, the shared-memory Stockham path the largest tile that fits.  0: does not fit.
+int fe_fft_pick_ft(int n_fft, int hop, int n_ch, int mode) {
+  const int E = fe_fft_fast_e(n_fft, hop);
+  if (E > 0) {
+    const size_t want = (E == 16 ? 113 : 56) * 1024;   // 2 CTAs / SM at 128 registers, 4 at 64
+    for (int ft = 32; ft >= 16; ft >>= 1)
+      if (fe_fft_smem_bytes(n_fft, hop, ft, n_ch, mode) <= want) return ft;
+    return fe_fft_smem_bytes(n_fft, hop, 16, n_ch, mode) <= 200 * 1024 ? 16 : 0;
+  }
+  for (int ft = 32; ft >= 4; ft >>= 1)
+    if (fe_fft_smem_bytes(n_fft, hop, ft, n_ch, mode) <= 200 * 1024) return ft;
+  return 0;
+}
+
 cudaError_t fe_launch_fft(const fe_fft_args& a_in, int mode, int64_t rows, cudaStream_t stream) {
   fe_fft_args a = a_in;
   a.fft_warps = fe_fft_warps_for(a.n_fft);
   const int n_ch = mode == 0 ? a.n_fft / 2 + 1 : a.n_filter;
-  const size_t smem = fe_fft_smem_bytes(a.n_fft, a.hop, a.ft, n_ch);
+  const size_t smem = fe_fft_smem_bytes(a.n_fft, a.hop, a.ft, n_ch, mode);
   const int64_t grid = rows * a.tiles_per_row;
   if (grid <= 0 || grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  cudaError_t e;
-  if (mode == 0) {
-    e = set_smem((const void*)fe_fft_kernel<0>, smem);
-    if (e != cudaSuccess) return e;
-    fe_fft_kernel<0><<<(unsigned)grid, kFftThreads, smem, stream>>>(a);
-  } else {
-    e = set_smem((const void*)fe_fft_kernel<1>, smem);
-    if (e != cudaSuccess) return e;
-    fe_fft_kernel<1><<<(unsigned)grid, kFftThreads, smem, stream>>>(a);
+  const int E = fe_fft_fast_e(a.n_fft, a.hop);
+  void (*kern)(fe_fft_args);
+  switch (E * 2 + (mode != 0)) {
+    case 8: kern = fe_rfft_kernel<0, 4>; break;
+    case 9: kern = fe_rfft_kernel<1, 4>; break;
+    case 16: kern = fe_rfft_kernel<0, 8>; break;
+    case 17: kern = fe_rfft_kernel<1, 8>; break;
+    case 32: kern = fe_rfft_kernel<0, 16>; break;
+    case 33: kern = fe_rfft_kernel<1, 16>; break;
+    case 0: kern = fe_fft_kernel<0>; break;
+    default: kern = fe_fft_kernel<1>; break;
   }
+  cudaError_t e = set_smem((const void*)kern, smem);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)grid, kFftThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

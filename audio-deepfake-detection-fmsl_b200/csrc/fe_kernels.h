@@ -35,7 +35,8 @@ struct fe_tail_args {
   float top_db;
 };
 
-size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch);
+size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch, int mode);
+int fe_fft_pick_ft(int n_fft, int hop, int n_ch, int mode);   // frames per CTA, 0: does not fit shared memory
 cudaError_t fe_launch_fft(const fe_fft_args& a, int mode, int64_t rows, cudaStream_t stream);
 size_t fe_tail_smem_bytes(const fe_tail_args& a);
 cudaError_t fe_launch_tail(const fe_tail_args& a, int64_t rows, cudaStream_t stream);

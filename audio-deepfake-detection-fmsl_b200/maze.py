@@ -125,6 +125,11 @@ class MazeScorer(nn.Module):
         return super().train(False)
 
     def classify(self, feats: Tensor) -> Tensor:
+        # fp32 convolutions (cuDNN would otherwise take TF32 on a B200 and move the scores by ~1e-2)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return self._classify(feats)
+
+    def _classify(self, feats: Tensor) -> Tensor:
         y = F.selu(self.first_bn(feats))
         y = self.se0(self.block0(y))
         for stage, gate in zip(self.res_blocks, self.se_blocks):

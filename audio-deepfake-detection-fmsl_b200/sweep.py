@@ -31,16 +31,18 @@ SEED = 1234                                # the reference's seed (maze5.py:449)
 def synthetic_block(block: int, device: torch.device, n_total: int = N_EVAL, n_bonafide: int = N_BONAFIDE,
                     seed: int = SEED) -> Tensor:
     """Utterances ``[block*1024, min(n_total, (block+1)*1024))`` as ``(n,64600)`` float32 on ``device``:
-    set S1 (``0.1*N(0,1)`` clipped to [-1,1]); bonafide utterances (the first ``n_bonafide``) at half the
-    amplitude so that the two classes are separable by a score and the EER is not a coin flip."""
+    set S1 (``0.1*N(0,1)`` clipped to [-1,1]) times a per-utterance log-normal gain whose median is 0.7 for
+    bonafide utterances (the first ``n_bonafide``) and 1.0 for spoofed ones: the two classes overlap, so the
+    EER is neither a coin flip nor 0 and reacts to small score changes."""
     g = torch.Generator(device=device)
     g.manual_seed(seed + 7919 * block)
     lo = block * BLOCK
     n = min(n_total, lo + BLOCK) - lo
     x = torch.randn((BLOCK, UTT_LEN), generator=g, device=device, dtype=torch.float32)[:n]
     x = (0.1 * x).clamp_(-1.0, 1.0)
+    gain = torch.exp(0.35 * torch.randn((BLOCK,), generator=g, device=device, dtype=torch.float32)[:n])
     idx = torch.arange(lo, lo + n, device=device)
-    return x * torch.where(idx < n_bonafide, 0.5, 1.0).unsqueeze(1)
+    return x * (gain * torch.where(idx < n_bonafide, 0.7, 1.0)).unsqueeze(1)
 
 
 def labels(n_total: int = N_EVAL, n_bonafide: int = N_BONAFIDE) -> np.ndarray:
