@@ -322,11 +322,10 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
     const fe_c2* gr = reinterpret_cast<const fe_c2*>(blob + h->off_rtwiddle);
     for (int i = tid; i <= NH / 2; i += kFftThreads) s_rtw[i] = gr[i];
   }
-  const float* bwp = reinterpret_cast<const float*>(blob + h->off_band_w);
-  if (MODE == 1 && h->total_w <= 2 * NFREQ + 2 * a.n_filter) {   // fe_rfft_bw_cap: weights fit the shared copy
-    for (int i = tid; i < h->total_w; i += kFftThreads) s_bw[i] = bwp[i];
-    bwp = s_bw;
-  }
+  const float* gbw = reinterpret_cast<const float*>(blob + h->off_band_w);
+  const bool bw_shared = MODE == 1 && h->total_w <= 2 * NFREQ + 2 * a.n_filter;   // fe_rfft_bw_cap
+  if (bw_shared)
+    for (int i = tid; i < h->total_w; i += kFftThreads) s_bw[i] = gbw[i];
   float2 tw2[E], twx[4];
 #pragma unroll
   for (int i = 0; i < E; ++i) {
@@ -352,7 +351,18 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
       clip_len = (int)a.T;
     }
     const int seg_here = (nf_here - 1) * hop + NFFT;
-    fe_stage_load(tid, kFftThreads, src, clip_len, (int)a.T, NFFT, t0 * hop, seg_here, a.preemph, s_stage);
+    // interior tile of a plain dense row (no reflection, no repeat, no pre-emphasis), 16-byte aligned: 128-bit copies
+    const int r0 = t0 * hop - NH;
+    const float* p0 = src + r0;
+    if (r0 >= 0 && r0 + seg_here <= (int)a.T && clip_len >= (int)a.T && a.preemph == 0.0f &&
+        (reinterpret_cast<uintptr_t>(p0) & 15) == 0 && (seg_here & 3) == 0) {
+      const float4* g4 = reinterpret_cast<const float4*>(p0);
+      float4* s4 = reinterpret_cast<float4*>(s_stage);
+#pragma unroll 4
+      for (int i = tid; i < seg_here / 4; i += kFftThreads) s4[i] = __ldg(g4 + i);
+    } else {
+      fe_stage_load(tid, kFftThreads, src, clip_len, (int)a.T, NFFT, t0 * hop, seg_here, a.preemph, s_stage);
+    }
   }
   __syncthreads();
 
@@ -374,11 +384,23 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
     const int32_t* bwoff = reinterpret_cast<const int32_t*>(blob + h->off_band_woff);
     for (int f = warp * fpw + sub; f < a.n_filter; f += kFftWarps * fpw) {
       const int s0 = bstart[f], len = blen[f];
-      const float* w = bwp + bwoff[f];
-      const float* pcol = s_pw + (size_t)s0 * stride + tl;
+      const float* pcol = s_pw + s0 * stride + tl;
       float acc = 0.0f;                                               // same summation order as fe_fbank_apply
-      for (int i = 0; i < len; ++i) acc = fmaf(pcol[(size_t)i * stride], w[i], acc);
-      s_tile[(size_t)f * stride + tl] = acc;
+      if (bw_shared) {
+        const float* w = s_bw + bwoff[f];
+        int i = 0;
+        for (; i + 4 <= len; i += 4) {
+          acc = fmaf(pcol[(i + 0) * stride], w[i + 0], acc);
+          acc = fmaf(pcol[(i + 1) * stride], w[i + 1], acc);
+          acc = fmaf(pcol[(i + 2) * stride], w[i + 2], acc);
+          acc = fmaf(pcol[(i + 3) * stride], w[i + 3], acc);
+        }
+        for (; i < len; ++i) acc = fmaf(pcol[i * stride], w[i], acc);
+      } else {
+        const float* w = gbw + bwoff[f];
+        for (int i = 0; i < len; ++i) acc = fmaf(pcol[i * stride], __ldg(w + i), acc);
+      }
+      s_tile[f * stride + tl] = acc;
     }
     __syncthreads();
     tile_src = s_tile;
