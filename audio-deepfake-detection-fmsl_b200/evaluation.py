@@ -25,16 +25,18 @@ def shard_range(n_total: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 def gather_scores(local_scores: torch.Tensor, n_total: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
     """All-gather the per-rank score blocks (padded to ``ceil(N/W)``) and trim to ``n_total``.
-    Every rank returns the full ``float32[n_total]`` vector in utterance order."""
+    Every rank returns the full ``float32[n_total]`` vector in utterance order (an ``int64`` input — the
+    per-utterance feature checksums of the sweep — is gathered as ``int64``)."""
+    dtype = torch.int64 if local_scores.dtype == torch.int64 else torch.float32
     if not (dist.is_available() and dist.is_initialized()):
         if local_scores.numel() != n_total:
             raise ValueError("single-process gather needs all scores")
-        return local_scores.to(torch.float32)
+        return local_scores.to(dtype)
     world = dist.get_world_size(group)
     per = -(-n_total // world)
-    buf = torch.zeros(per, dtype=torch.float32, device=local_scores.device)
-    buf[: local_scores.numel()] = local_scores.to(torch.float32)
-    out = torch.empty(world * per, dtype=torch.float32, device=local_scores.device)
+    buf = torch.zeros(per, dtype=dtype, device=local_scores.device)
+    buf[: local_scores.numel()] = local_scores.to(dtype)
+    out = torch.empty(world * per, dtype=dtype, device=local_scores.device)
     dist.all_gather_into_tensor(out, buf, group=group)
     return out[:n_total]
 

@@ -6,8 +6,9 @@ GPUs of one box, LFCC+delta+delta-delta front-end -> maze5 classifier (seeded we
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         --master-port 29511 sweep.py                                      # one rank per GPU, NCCL gather
 
-Rank 0 prints ONE JSON line: EER / min-DCF, a SHA-256 of the gathered score vector (identical for every world
-size), front-end-only and end-to-end utterances/s (max over ranks of the device time of the local shard).
+Rank 0 prints ONE JSON line: EER / min-DCF, a SHA-256 of the gathered per-utterance feature checksums (identical
+for every world size and batch size), a SHA-256 of the score vector (stock cuDNN classifier: identical for
+identical batch shapes), front-end-only and end-to-end utterances/s (max over ranks of the device time of the local shard).
 """
 import argparse
 import json
@@ -71,7 +72,7 @@ def main():
                         f"LFCC+delta+delta-delta -> maze5{'-FMSL' if args.fmsl else ''} classifier -> gather -> EER",
             "n_gpus": world, "batch": args.batch, "variant": frontend.engine.resolved_variant(),
             "eer": r["eer"], "min_dcf": r["min_dcf"], "eer_threshold": r["eer_threshold"],
-            "scores_sha256": r["scores_sha256"],
+            "scores_sha256": r["scores_sha256"], "features_sha256": r["features_sha256"],
             "frontend_utt_per_s": n_total / (fe_ms * 1e-3), "frontend_ms": fe_ms,
             "frontend_plus_classifier_utt_per_s": n_total / (dev_ms * 1e-3), "device_ms": dev_ms,
             "sweep_wall_utt_per_s": n_total / (wall_ms * 1e-3), "wall_ms": wall_ms,

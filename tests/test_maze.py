@@ -111,6 +111,7 @@ def test_config4_sweep_sample_matches_reference_features(fe):
     r2 = sweep.run_sweep(front, scorer, dev, n_total=n, n_bonafide=nb, batch=256)
     # cuDNN picks its convolution algorithm per batch size: fp32 summation order changes, nothing else
     assert np.abs(r["scores"] - r2["scores"]).max() <= SCORE_TOL and abs(r["eer"] - r2["eer"]) <= 2.0 / n
+    assert r["features_sha256"] == r2["features_sha256"]      # the front-end itself is batch-invariant bit for bit
     # reference CPU features for a 256-utterance sample of the same sweep (both classes present)
     idx = np.r_[0:128, 1024:1152]
     x = torch.cat([sweep.synthetic_block(0, dev, n, nb)[:128], sweep.synthetic_block(1, dev, n, nb)[:128]]).cpu()
