@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
   float* s_tile = reinterpret_cast<float*>(smem_raw + off);  // MODE 1: [n_filter][ft+1]
   off += (MODE == 1) ? ((((size_t)a.n_filter * stride * 4) + 15) & ~(size_t)15) : 0;
   float* s_bw = reinterpret_cast<float*>(smem_raw + off);    // MODE 1: band weights
+  off += (MODE == 1) ? (size_t)(2 * NFREQ + 2 * a.n_filter) * 4 : 0;
+  int4* s_band = reinterpret_cast<int4*>(smem_raw + ((off + 15) & ~(size_t)15));   // MODE 1: {start, len, weight offset}
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row_local = blockIdx.x / a.tiles_per_row;
@@ -326,6 +328,12 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
   const bool bw_shared = MODE == 1 && h->total_w <= 2 * NFREQ + 2 * a.n_filter;   // fe_rfft_bw_cap
   if (bw_shared)
     for (int i = tid; i < h->total_w; i += kFftThreads) s_bw[i] = gbw[i];
+  if (MODE == 1) {
+    const int32_t* bstart = reinterpret_cast<const int32_t*>(blob + h->off_band_start);
+    const int32_t* blen = reinterpret_cast<const int32_t*>(blob + h->off_band_len);
+    const int32_t* bwoff = reinterpret_cast<const int32_t*>(blob + h->off_band_woff);
+    for (int f = tid; f < a.n_filter; f += kFftThreads) s_band[f] = make_int4(bstart[f], blen[f], bwoff[f], 0);
+  }
   float2 tw2[E], twx[4];
 #pragma unroll
   for (int i = 0; i < E; ++i) {
@@ -379,15 +387,13 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
   int n_ch = NFREQ;
   const int tl = lane & (ft - 1), sub = lane / ft, fpw = 32 / ft;     // ft is 16 or 32
   if (MODE == 1) {
-    const int32_t* bstart = reinterpret_cast<const int32_t*>(blob + h->off_band_start);
-    const int32_t* blen = reinterpret_cast<const int32_t*>(blob + h->off_band_len);
-    const int32_t* bwoff = reinterpret_cast<const int32_t*>(blob + h->off_band_woff);
     for (int f = warp * fpw + sub; f < a.n_filter; f += kFftWarps * fpw) {
-      const int s0 = bstart[f], len = blen[f];
+      const int4 band = s_band[f];
+      const int s0 = band.x, len = band.y;
       const float* pcol = s_pw + s0 * stride + tl;
       float acc = 0.0f;                                               // same summation order as fe_fbank_apply
       if (bw_shared) {
-        const float* w = s_bw + bwoff[f];
+        const float* w = s_bw + band.z;
         int i = 0;
         for (; i + 4 <= len; i += 4) {
           acc = fmaf(pcol[(i + 0) * stride], w[i + 0], acc);
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
         }
         for (; i < len; ++i) acc = fmaf(pcol[i * stride], w[i], acc);
       } else {
-        const float* w = gbw + bwoff[f];
+        const float* w = gbw + band.z;
         for (int i = 0; i < len; ++i) acc = fmaf(pcol[i * stride], __ldg(w + i), acc);
       }
       s_tile[f * stride + tl] = acc;
@@ -744,7 +750,9 @@ size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch, int mode) {
     b += (size_t)n_fft * 4 + ((((size_t)(nh / 2 + 1)) * 8 + 15) & ~(size_t)15);
     b += (size_t)kFftWarps * zunits * 8;
     b += (((size_t)(nh + 1) * (ft + 1) * 4) + 15) & ~(size_t)15;
-    if (mode == 1) b += ((((size_t)n_ch * (ft + 1) * 4) + 15) & ~(size_t)15) + (size_t)fe_rfft_bw_cap(n_fft, n_ch) * 4;
+    if (mode == 1)
+      b += ((((size_t)n_ch * (ft + 1) * 4) + 15) & ~(size_t)15) + (size_t)fe_rfft_bw_cap(n_fft, n_ch) * 4 + 16 +
+           (size_t)n_ch * 16;
     return b;
   }
   b += (size_t)n_fft * 4 + (size_t)nh * 8 + ((((size_t)(nh / 2 + 1)) * 8 + 15) & ~(size_t)15);

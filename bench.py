@@ -24,6 +24,7 @@ if ROOT not in sys.path:
 
 UTT_LEN = 64600
 NCU_DRAM_BYTES_PER_UTT_STREAM = 287700  # fe_stream_kernel: (307.0 MB read + 33.65 MB written) / 1184 utterances
+NCU_DRAM_BYTES_PER_UTT_RFFT_MEL = 309900  # fe_rfft_kernel<1,16>: (145.6 MB read + 28.9 MB written) / 563 utterances
 SEED = 1234  # the reference's default seed (maze5.py:449)
 
 WORKLOADS = {
@@ -284,13 +285,19 @@ def main():
     # DRAM traffic of the dominant kernel per launch, from the ncu --set full capture of the same kernel
     # (profiles/r1_stream_final_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum over 1184 utterances)
     traffic = None
+    traffic_src = None
     if variant == "dft_gemm" and args.workload == "lfcc":
         traffic = NCU_DRAM_BYTES_PER_UTT_STREAM * B / max(1, int(dom_launches))
+        traffic_src = "profiles/r1_stream_final_summary.txt"
+    elif variant == "fft" and args.workload == "mel":
+        traffic = NCU_DRAM_BYTES_PER_UTT_RFFT_MEL * B / max(1, int(dom_launches))
+        traffic_src = "profiles/r1_rfft_mel_summary.txt"
     roofline = {
         "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
-        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per utterance x utterances per launch (profiles/r1_stream_final_summary.txt)" if traffic else None,
+        "traffic_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per utterance x utterances per launch ({traffic_src})" if traffic else None,
         "peak_source": peak_src,
-        "kernel": ("fe_stream_kernel" if variant == "dft_gemm" else "fe_fft_kernel<1>"),
+        "kernel": ("fe_stream_kernel" if variant == "dft_gemm" else
+                   ("fe_rfft_kernel<1,16>" if args.workload == "mel" else "fe_rfft_kernel<1,8>")),
         "kernel_ms_per_step": dom_ms, "kernel_launches_per_step": int(dom_launches),
         "kernel_share_of_step": dom_ms / ms_per_step,
         "algorithmic_bytes_per_utt": W["bytes_per_utt"],
