@@ -284,7 +284,7 @@ template <int E>
 __host__ __device__ constexpr int fe_rfft_zunits() { return 32 * E - 1 + ((32 * E - 1) >> fe_ilog2(E)) + ((32 * E - 1) >> (fe_ilog2(E) + 4)) + 1; }
 
 template <int MODE, int E>
-__global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
+__global__ void __launch_bounds__(kFftThreads, E == 16 ? 2 : 4) fe_rfft_kernel(fe_fft_args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NH = 32 * E, NFFT = 2 * NH, NFREQ = NH + 1;
   const int hop = a.hop, ft = a.ft, stride = ft + 1;
@@ -307,11 +307,6 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
   int4* s_band = reinterpret_cast<int4*>(smem_raw + ((off + 15) & ~(size_t)15));   // MODE 1: {start, len, weight offset}
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t row_local = blockIdx.x / a.tiles_per_row;
-  const int tile = blockIdx.x - (int)(row_local * a.tiles_per_row);
-  const int64_t row = a.row_base + row_local;
-  const int t0 = tile * ft;
-  const int nf_here = min(ft, a.n_frames - t0);
 
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
@@ -347,6 +342,18 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
     twx[s] = (lane & half) ? make_float2(t.x, t.y) : make_float2(1.0f, 0.0f);
   }
 
+  float2* zbuf = s_z + (size_t)warp * fe_rfft_zunits<E>();
+  const int tl = lane & (ft - 1), sub = lane / ft, fpw = 32 / ft;     // ft is 16 or 32
+  __shared__ float s_red[kFftWarps];
+
+  // ---- persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... (constants above are loaded once) ----
+  for (int64_t blk = blockIdx.x; blk < a.n_blocks; blk += gridDim.x) {
+  const int64_t row_local = blk / a.tiles_per_row;
+  const int tile = (int)(blk - row_local * a.tiles_per_row);
+  const int64_t row = a.row_base + row_local;
+  const int t0 = tile * ft;
+  const int nf_here = min(ft, a.n_frames - t0);
+
   // ---- stage the waveform segment (as fe_fft_kernel) ----------------------------------------------
   {
     const float* src;
@@ -375,7 +382,6 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
   __syncthreads();
 
   // ---- one warp = one frame: FFT in registers, powers into the [bin][frame] tile -------------------
-  float2* zbuf = s_z + (size_t)warp * fe_rfft_zunits<E>();
   for (int fl = warp; fl < nf_here; fl += kFftWarps) {
     fe_warp_rfft_power<E>(lane, s_stage + (size_t)fl * hop, s_win, tw2, twx, s_rtw, zbuf, s_pw + fl, stride);
     __syncwarp();
@@ -385,7 +391,6 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
   // ---- filterbank: lane -> (filter slot, frame); the band loop has the same length for a whole warp step ----
   const float* tile_src = s_pw;
   int n_ch = NFREQ;
-  const int tl = lane & (ft - 1), sub = lane / ft, fpw = 32 / ft;     // ft is 16 or 32
   if (MODE == 1) {
     for (int f = warp * fpw + sub; f < a.n_filter; f += kFftWarps * fpw) {
       const int4 band = s_band[f];
@@ -425,7 +430,6 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
   }
   if (MODE == 1 && a.group_max) {
     vmax = warp_max(vmax);
-    __shared__ float s_red[kFftWarps];
     if (lane == 0) s_red[warp] = vmax;
     __syncthreads();
     if (tid == 0) {
@@ -434,6 +438,8 @@ __global__ void __launch_bounds__(kFftThreads) fe_rfft_kernel(fe_fft_args a) {
       for (int w = 1; w < kFftWarps; ++w) m = fmaxf(m, s_red[w]);
       atomicMax(a.group_max + row / a.top_db_group, __float_as_uint(m));
     }
+  }
+  __syncthreads();   // the next tile reuses the staging buffer, the tiles and s_red
   }
 }
 
@@ -797,7 +803,22 @@ cudaError_t fe_launch_fft(const fe_fft_args& a_in, int mode, int64_t rows, cudaS
   }
   cudaError_t e = set_smem((const void*)kern, smem);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)grid, kFftThreads, smem, stream>>>(a);
+  int64_t launch_grid = grid;
+  if (E > 0) {   // persistent CTAs: as many as are resident at once
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFftThreads, smem);
+    if (e != cudaSuccess) return e;
+    a.n_blocks = grid;
+    const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+    if (launch_grid > resident) launch_grid = resident;
+  }
+  kern<<<(unsigned)launch_grid, kFftThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@ struct fe_fft_args {
   unsigned int* group_max;  // per top_db group maximum energy (float bits), NULL when not needed
   int64_t T;
   int64_t row_base;         // absolute index of the launch's first row
+  int64_t n_blocks;         // fe_rfft_kernel: (row, tile) work items of the launch (set by fe_launch_fft)
   int32_t n_fft, hop, n_frames, n_filter;
   int32_t ft;               // frames per CTA
   int32_t tiles_per_row;
