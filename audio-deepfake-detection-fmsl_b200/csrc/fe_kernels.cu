@@ -724,6 +724,37 @@ __global__ void __launch_bounds__(256) fe_dense_rows_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fe_tail_pointwise_kernel : the tail when there is no DCT and no deltas (mel features): out = log/dB(energies)
+// element by element with the arithmetic of fe_tail_load; a row's [n_filter][n_frames] block is contiguous on
+// both sides.  grid (blocks per row, rows), 4 elements per thread, coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fe_tail_pointwise_kernel(fe_tail_args a) {
+  const int64_t row_local = blockIdx.y, row = a.row_base + row_local;
+  const int per_row = a.n_filter * a.n_frames;
+  float floor_db = -INFINITY;
+  if (a.log_mode == B200FE_LOG_DB && a.top_db >= 0.0f) {
+    const float gmax = __uint_as_float(a.group_max[row / a.top_db_group]);
+    floor_db = 10.0f * log10f(fmaxf(gmax, 1e-10f)) - a.top_db;
+  }
+  const float* src = a.energies + (size_t)row_local * per_row;
+  float* dst = a.out + (size_t)row * per_row;
+  const int i0 = blockIdx.x * 1024 + threadIdx.x;
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] = (i0 + 256 * u < per_row) ? src[i0 + 256 * u] : 1.0f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float x = v[u];
+    if (a.log_mode == B200FE_LOG_DB) {
+      x = fmaxf(10.0f * log10f(fmaxf(x, 1e-10f)), floor_db);
+    } else if (a.log_mode == B200FE_LOG_LN) {
+      x = logf(x + 1e-6f);
+    }
+    if (i0 + 256 * u < per_row) dst[i0 + 256 * u] = x;
+  }
+}
+
 cudaError_t set_smem(const void* fn, size_t bytes) {
   if (bytes <= 48 * 1024) return cudaSuccess;
   return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -879,6 +910,20 @@ static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cuda
 }
 
 cudaError_t fe_launch_tail(const fe_tail_args& a, int64_t rows, cudaStream_t stream) {
+  if (a.n_coef == 0 && a.deltas == 0 && !a.force_generic) {
+    const int per_row = a.n_filter * a.n_frames;
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+      fe_tail_args b = a;
+      const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+      b.row_base = a.row_base + r0;
+      b.energies = a.energies + (size_t)r0 * per_row;
+      dim3 grid((unsigned)((per_row + 1023) / 1024), (unsigned)nr);
+      fe_tail_pointwise_kernel<<<grid, 256, 0, stream>>>(b);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   if (a.n_filter <= kFastMax && a.n_coef <= kFastMax && !a.force_generic) return launch_tail_fast(a, rows, stream);
   const size_t smem = fe_tail_smem_bytes(a);
   cudaError_t e = set_smem((const void*)fe_tail_kernel, smem);

@@ -52,6 +52,14 @@ def read_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def read_tensor_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst; fp16 runs at the same rate)"
+    except Exception:
+        return 2250.0, "fallback (nominal dense bf16/fp16)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -303,6 +311,16 @@ def main():
         "algorithmic_bytes_per_utt": W["bytes_per_utt"],
         "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak,
     }
+    if variant == "dft_gemm":
+        # the tensor-pipe view of the DFT-GEMM variant.  Executed flops: four folded, parity-split
+        # sub-GEMMs [128 frames x win/4] x [win/4 x n_fft/4], three fp16 MMAs each (hi*hi + lo*hi + hi*lo).
+        win, n_fft = 320, 512
+        flops_per_frame = 4 * 3 * 2 * (win // 4) * (n_fft // 4)
+        tpeak, tsrc = read_tensor_peak()
+        tf = B * W["n_frames"] * flops_per_frame / (dom_ms / 1000.0) / 1e12
+        roofline["tensor_view"] = {"executed_flops_per_utt": W["n_frames"] * flops_per_frame, "achieved": tf, "peak": tpeak,
+                                   "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": tsrc,
+                                   "dense_dft_flops_per_utt": 2 * W["n_frames"] * win * (n_fft + 2)}
     cpu_baseline = None
     if not args.no_cpu_baseline:
         thr, threads, n = cpu_reference_throughput(args.workload, args.cpu_budget)

@@ -50,7 +50,16 @@ def test_geometry_queries(fe):
     p = _params(fe)
     assert lib.b200fe_n_frames(C.byref(p), 64600) == 404
     assert lib.b200fe_n_out_channels(C.byref(p)) == 60
-    assert lib.b200fe_workspace_bytes(C.byref(p), 4096, 64600) > 0
+    ws = lib.b200fe_workspace_bytes(C.byref(p), 4096, 64600)
+    assert ws > 0 and lib.b200fe_workspace_bytes_ex(C.byref(p), 4096, 64600, 0) == ws
+    # ragged clips / pre-emphasised input on the tensor-core variant: one chunk of dense rows more
+    g = _params(fe, variant=fe._lib.VARIANT_DFT_GEMM)
+    base = lib.b200fe_workspace_bytes_ex(C.byref(g), 4096, 64600, 0)
+    ragged = lib.b200fe_workspace_bytes_ex(C.byref(g), 4096, 64600, 1)
+    assert 0 < ragged - base <= 4096 * 64600 * 4 + 256 and (ragged - base) % (64600 * 4) < 256
+    assert lib.b200fe_workspace_bytes_ex(C.byref(_params(fe, variant=fe._lib.VARIANT_DFT_GEMM, preemph=0.97)), 4096, 64600, 0) == ragged
+    assert lib.b200fe_workspace_bytes_ex(C.byref(_params(fe, variant=fe._lib.VARIANT_FFT)), 4096, 64600, 1) == \
+        lib.b200fe_workspace_bytes_ex(C.byref(_params(fe, variant=fe._lib.VARIANT_FFT)), 4096, 64600, 0)
     q = _params(fe, n_fft=1024, win_length=1024, hop_length=256, n_filter=80, n_coef=0, deltas=0)
     assert lib.b200fe_n_frames(C.byref(q), 64600) == 253
     assert lib.b200fe_n_out_channels(C.byref(q)) == 80

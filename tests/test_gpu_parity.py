@@ -419,3 +419,36 @@ def test_fast_tail_equals_generic_tail(fe, monkeypatch):
     fast = m(short).clone()
     monkeypatch.setenv("B200FE_GENERIC_TAIL", "1")
     assert feat_err(fast.cpu().numpy(), m(short).cpu().numpy()).max() <= 5e-5
+
+
+def test_pointwise_tail_equals_generic_tail(fe, monkeypatch):
+    """Mel features (no DCT, no deltas) take fe_tail_pointwise_kernel; it repeats fe_tail_kernel's arithmetic."""
+    x = cuda(np.concatenate([synth.s1_noise(3), synth.s2_speechlike(2), synth.s3_edge()], 0))
+    for log in ("db", "log", None):
+        m = fe.MelSpectrogram(**MEL_CFG, log=log)
+        monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
+        fast = m(x).clone()
+        monkeypatch.setenv("B200FE_GENERIC_TAIL", "1")
+        generic = m(x).clone()
+        monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
+        assert torch.equal(fast, generic), log
+
+
+@pytest.mark.parametrize("n_fft,win,hop", [(256, 128, 64), (512, 320, 160), (1024, 1024, 256), (1024, 400, 200)])
+def test_warp_fft_equals_stockham_fft(fe, monkeypatch, n_fft, win, hop):
+    """fe_rfft_kernel (register-resident warp FFT, CTA-wide filterbank) against fe_fft_kernel (shared-memory
+    Stockham stages, the kernel the CPU emulation mirrors): power spectra to fp32 rounding, and both against the
+    oracle's float64 rfft."""
+    x = np.concatenate([synth.s1_noise(3, 20000), synth.s2_speechlike(2, 20000)], 0)
+    m = fe.Spectrogram(n_fft=n_fft, win_length=win, hop_length=hop)
+    monkeypatch.delenv("B200FE_SMEM_FFT", raising=False)
+    a = m(cuda(x)).cpu().numpy()
+    monkeypatch.setenv("B200FE_SMEM_FFT", "1")
+    b = m(cuda(x)).cpu().numpy()
+    monkeypatch.delenv("B200FE_SMEM_FFT", raising=False)
+    ref = torch.stft(torch.from_numpy(x).double(), n_fft, hop, win, window=torch.hann_window(win, dtype=torch.float64),
+                     center=True, pad_mode="reflect", return_complex=True).abs().pow(2).numpy()
+    assert a.shape == b.shape == ref.shape
+    for r in range(x.shape[0]):
+        scale = ref[r].max()
+        assert np.abs(a[r] - ref[r]).max() <= 4e-6 * scale and np.abs(b[r] - ref[r]).max() <= 4e-6 * scale, r
