@@ -34,6 +34,13 @@ WORKLOADS = {
         batch=4096, n_out=60, n_frames=404,
         bytes_per_utt=UTT_LEN * 4 + 60 * 404 * 4,  # 355,360 B: waveform read once + features written once
     ),
+    # BASELINE.json configs[4] input contract: variable-length clips (1-10 s), repeat-pad / truncate to 64600 fused
+    # into the front-end (not the headline; front-end only, the classifier is timed by sweep.py)
+    "lfcc_ragged": dict(
+        name="LFCC(20)+delta+delta-delta on 4096 ragged clips of 16000..160000 samples, repeat-pad to 64600 fused (BASELINE config 5 input)",
+        batch=4096, n_out=60, n_frames=404,
+        bytes_per_utt=UTT_LEN * 4 + 60 * 404 * 4,  # replaced by the clips' actual bytes below
+    ),
     # BASELINE.json configs[2] (not the headline; selectable for measurements)
     "mel": dict(
         name="80-bin log-mel (dB), n_fft=1024 hop=256, batch 8192 x 64600 samples (BASELINE config 3)",
@@ -105,7 +112,7 @@ class ClockSampler:
 
 def make_modules(workload, variant):
     import b200_frontend as fe
-    if workload == "lfcc":
+    if workload in ("lfcc", "lfcc_ragged"):
         return fe.LFCCDelta(16000, n_filter=20, n_lfcc=20, speckwargs=dict(n_fft=512, win_length=320, hop_length=160),
                             variant=variant)
     return fe.MelSpectrogram(16000, n_fft=1024, hop_length=256, n_mels=80, log="db", variant=variant)
@@ -113,7 +120,7 @@ def make_modules(workload, variant):
 
 def make_reference(workload):
     from oracle.torchaudio_ref import LFCCDeltaRef, LogMelRef
-    return LFCCDeltaRef() if workload == "lfcc" else LogMelRef()
+    return LFCCDeltaRef() if workload.startswith("lfcc") else LogMelRef()
 
 
 def cpu_reference_throughput(workload, budget_s, batch=64, max_batches=10_000, threads=None):
@@ -158,7 +165,7 @@ def run_reference_arm(args):
     value = total_n / total_t
     line = {
         "impl": "reference", "metric": "utterances/sec (4 s, 16 kHz) LFCC+delta+delta-delta front-end"
-        if args.workload == "lfcc" else "utterances/sec (4 s, 16 kHz) 80-bin log-mel front-end",
+        if args.workload.startswith("lfcc") else "utterances/sec (4 s, 16 kHz) 80-bin log-mel front-end",
         "value": value, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -213,12 +220,27 @@ def main():
     n_sets = 3
     gen = torch.Generator(device=dev)
     gen.manual_seed(SEED + rank)
-    waves = [(0.1 * torch.randn(B, UTT_LEN, device=dev, generator=gen)).clamp_(-1.0, 1.0) for _ in range(n_sets)]
+    ragged = args.workload == "lfcc_ragged"
     outs = [torch.empty(B, W["n_out"], W["n_frames"], device=dev) for _ in range(n_sets)]
     energies = torch.empty(B, eng.params.n_filter, W["n_frames"], device=dev)
+    if ragged:
+        # set S4: clip lengths U{16000..160000}, flat buffer + offsets
+        lengths = [torch.randint(16000, 160001, (B,), device=dev, generator=gen, dtype=torch.int32) for _ in range(n_sets)]
+        offsets = [torch.cumsum(l.to(torch.int64), 0) - l.to(torch.int64) for l in lengths]
+        waves = [(0.1 * torch.randn(int(l.sum().item()), device=dev, generator=gen)).clamp_(-1.0, 1.0) for l in lengths]
+        read = sum(float(l.clamp(max=UTT_LEN).sum().item()) for l in lengths) / (n_sets * B)
+        W["bytes_per_utt"] = int(read * 4 + W["n_out"] * W["n_frames"] * 4)   # samples actually read once + features
+        args.no_e2e = True
+        args.no_cpu_baseline = True
 
-    def step(i):
-        eng.features(waves[i % n_sets], out=outs[i % n_sets])
+        def step(i):
+            j = i % n_sets
+            eng.features(waves[j], out=outs[j], offsets=offsets[j], lengths=lengths[j], T=UTT_LEN)
+    else:
+        waves = [(0.1 * torch.randn(B, UTT_LEN, device=dev, generator=gen)).clamp_(-1.0, 1.0) for _ in range(n_sets)]
+
+        def step(i):
+            eng.features(waves[i % n_sets], out=outs[i % n_sets])
 
     for i in range(WU):
         step(i)
@@ -240,16 +262,19 @@ def main():
             dist.barrier()
         elapsed_ms = ev0.elapsed_time(ev1)
         # dominant kernel alone (same launches as inside the step), for the roofline line
-        for i in range(2):
-            eng.fbank_energies(waves[i % n_sets], out=energies)
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for i in range(K):
-            eng.fbank_energies(waves[i % n_sets], out=energies)
-        k1.record()
-        torch.cuda.synchronize()
-        dom_launches = eng.last_launch_count()
-        dom_ms = k0.elapsed_time(k1) / K
+        if ragged:   # dense-rows kernel + streaming kernel + tail are reported together
+            dom_launches, dom_ms = launches_per_step, elapsed_ms / K
+        else:
+            for i in range(2):
+                eng.fbank_energies(waves[i % n_sets], out=energies)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for i in range(K):
+                eng.fbank_energies(waves[i % n_sets], out=energies)
+            k1.record()
+            torch.cuda.synchronize()
+            dom_launches = eng.last_launch_count()
+            dom_ms = k0.elapsed_time(k1) / K
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,14 +329,15 @@ def main():
         "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
         "traffic_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per utterance x utterances per launch ({traffic_src})" if traffic else None,
         "peak_source": peak_src,
-        "kernel": ("fe_stream_kernel" if variant == "dft_gemm" else
+        "kernel": ("fe_dense_rows_kernel + fe_stream_kernel + fe_tail_fast_kernel (whole step)" if ragged else
+                   "fe_stream_kernel" if variant == "dft_gemm" else
                    ("fe_rfft_kernel<1,16>" if args.workload == "mel" else "fe_rfft_kernel<1,8>")),
         "kernel_ms_per_step": dom_ms, "kernel_launches_per_step": int(dom_launches),
         "kernel_share_of_step": dom_ms / ms_per_step,
         "algorithmic_bytes_per_utt": W["bytes_per_utt"],
         "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak,
     }
-    if variant == "dft_gemm":
+    if variant == "dft_gemm" and not ragged:
         # the tensor-pipe view of the DFT-GEMM variant.  Executed flops: four folded, parity-split
         # sub-GEMMs [128 frames x win/4] x [win/4 x n_fft/4], three fp16 MMAs each (hi*hi + lo*hi + hi*lo).
         win, n_fft = 320, 512
@@ -328,7 +354,7 @@ def main():
                         "sample": f"torchaudio {args.workload} path on host, {n} S1 utterances in B=64 chunks, "
                                   f"{threads} threads ({os.cpu_count()} logical cores)"}
     line = {
-        "metric": "utterances/sec (4 s, 16 kHz) LFCC+delta+delta-delta front-end" if args.workload == "lfcc"
+        "metric": "utterances/sec (4 s, 16 kHz) LFCC+delta+delta-delta front-end" if args.workload.startswith("lfcc")
         else "utterances/sec (4 s, 16 kHz) 80-bin log-mel front-end",
         "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": WU,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
