@@ -452,3 +452,24 @@ def test_warp_fft_equals_stockham_fft(fe, monkeypatch, n_fft, win, hop):
     for r in range(x.shape[0]):
         scale = ref[r].max()
         assert np.abs(a[r] - ref[r]).max() <= 4e-6 * scale and np.abs(b[r] - ref[r]).max() <= 4e-6 * scale, r
+
+
+def test_ragged_tiny_and_long_clips(fe):
+    """pad() semantics at the extremes (maze5.py:280-285): clips of 1, 7 and 100 samples are tiled thousands of
+    times, a clip of exactly 64600 is taken as is, longer ones are truncated; both kernel families."""
+    rs = np.random.RandomState(5)
+    lens = np.array([1, 7, 100, 64599, 64600, 64601, 160000], dtype=np.int32)
+    clips = [np.clip(0.1 * rs.standard_normal(l), -1, 1).astype(np.float32) for l in lens]
+    clips[0][:] = 0.25          # a constant signal: energy only in the lowest band
+    flat = np.concatenate(clips)
+    offsets = (np.cumsum(lens.astype(np.int64)) - lens).astype(np.int64)
+    dense = np.stack([O.pad_repeat(c, 64600) for c in clips])
+    ref = LFCCDeltaRef()(torch.from_numpy(dense)).numpy()
+    for variant in ("fft", "auto"):
+        m = fe.LFCCDelta(**LFCC_CFG, variant=variant)
+        out = m.forward_ragged(cuda(flat), cuda(offsets), cuda(lens), 64600)
+        assert torch.equal(out, m(cuda(dense))), variant
+        assert_feat_close(out.cpu().numpy()[1:], ref[1:], TOL_TONAL, f"tiny/long clips ({variant})")
+        # the constant clip sits on the top_db floor almost everywhere: compare where the reference is above it
+        a, b = out.cpu().numpy()[0], ref[0]
+        assert np.isfinite(a).all() and np.abs(a[0] - b[0]).max() <= 1e-3 * max(1.0, np.abs(b[0]).max())
