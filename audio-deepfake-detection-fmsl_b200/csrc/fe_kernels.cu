@@ -346,6 +346,40 @@ __global__ void __launch_bounds__(kFftThreads, E == 16 ? 2 : 4) fe_rfft_kernel(f
   const int tl = lane & (ft - 1), sub = lane / ft, fpw = 32 / ft;     // ft is 16 or 32
   __shared__ float s_red[kFftWarps];
 
+  // Staging of work item `b` into s_stage.  Interior tiles of plain dense rows (no reflection, no repeat, no
+  // pre-emphasis, 16-byte aligned) are 128-bit copies, asynchronous (cp.async) on request; everything else goes
+  // through fe_stage_load.  Returns true when the copy was issued (or done); async_only: false = nothing was done.
+  auto stage_tile = [&](int64_t b, bool async_only) -> bool {
+    const int64_t rl = b / a.tiles_per_row;
+    const int tile_b = (int)(b - rl * a.tiles_per_row);
+    const int64_t row_b = a.row_base + rl;
+    const int t0_b = tile_b * ft;
+    const int nf_b = min(ft, a.n_frames - t0_b);
+    const float* src;
+    int clip_len;
+    if (a.offsets) {
+      src = a.wave + a.offsets[row_b];
+      clip_len = a.lengths[row_b];
+    } else {
+      src = a.wave + row_b * a.T;
+      clip_len = (int)a.T;
+    }
+    const int seg_here = (nf_b - 1) * hop + NFFT;
+    const int r0 = t0_b * hop - NH;
+    const float* p0 = src + r0;
+    if (r0 >= 0 && r0 + seg_here <= (int)a.T && clip_len >= (int)a.T && a.preemph == 0.0f &&
+        (reinterpret_cast<uintptr_t>(p0) & 15) == 0 && (seg_here & 3) == 0) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stage);
+      for (int i = tid; i < seg_here / 4; i += kFftThreads)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(p0 + 4 * i) : "memory");
+      return true;
+    }
+    if (async_only) return false;
+    fe_stage_load(tid, kFftThreads, src, clip_len, (int)a.T, NFFT, t0_b * hop, seg_here, a.preemph, s_stage);
+    return true;
+  };
+  bool prefetched = false;
+
   // ---- persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... (constants above are loaded once) ----
   for (int64_t blk = blockIdx.x; blk < a.n_blocks; blk += gridDim.x) {
   const int64_t row_local = blk / a.tiles_per_row;
@@ -354,31 +388,9 @@ __global__ void __launch_bounds__(kFftThreads, E == 16 ? 2 : 4) fe_rfft_kernel(f
   const int t0 = tile * ft;
   const int nf_here = min(ft, a.n_frames - t0);
 
-  // ---- stage the waveform segment (as fe_fft_kernel) ----------------------------------------------
-  {
-    const float* src;
-    int clip_len;
-    if (a.offsets) {
-      src = a.wave + a.offsets[row];
-      clip_len = a.lengths[row];
-    } else {
-      src = a.wave + row * a.T;
-      clip_len = (int)a.T;
-    }
-    const int seg_here = (nf_here - 1) * hop + NFFT;
-    // interior tile of a plain dense row (no reflection, no repeat, no pre-emphasis), 16-byte aligned: 128-bit copies
-    const int r0 = t0 * hop - NH;
-    const float* p0 = src + r0;
-    if (r0 >= 0 && r0 + seg_here <= (int)a.T && clip_len >= (int)a.T && a.preemph == 0.0f &&
-        (reinterpret_cast<uintptr_t>(p0) & 15) == 0 && (seg_here & 3) == 0) {
-      const float4* g4 = reinterpret_cast<const float4*>(p0);
-      float4* s4 = reinterpret_cast<float4*>(s_stage);
-#pragma unroll 4
-      for (int i = tid; i < seg_here / 4; i += kFftThreads) s4[i] = __ldg(g4 + i);
-    } else {
-      fe_stage_load(tid, kFftThreads, src, clip_len, (int)a.T, NFFT, t0 * hop, seg_here, a.preemph, s_stage);
-    }
-  }
+  // ---- the waveform segment: staged here unless the previous iteration prefetched it (cp.async) ------
+  if (!prefetched) stage_tile(blk, false);
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   // ---- one warp = one frame: FFT in registers, powers into the [bin][frame] tile -------------------
@@ -387,6 +399,8 @@ __global__ void __launch_bounds__(kFftThreads, E == 16 ? 2 : 4) fe_rfft_kernel(f
     __syncwarp();
   }
   __syncthreads();
+  // the staging buffer is free: fetch the next work item's samples behind the filterbank and store phases
+  prefetched = (blk + gridDim.x < a.n_blocks) && stage_tile(blk + gridDim.x, true);
 
   // ---- filterbank: lane -> (filter slot, frame); the band loop has the same length for a whole warp step ----
   const float* tile_src = s_pw;
