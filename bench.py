@@ -68,28 +68,67 @@ def read_tensor_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process (a sample every ~5 ms) when
+    pynvml imports, else one `nvidia-smi` query per sample (the recipe's clocks line)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []   # (sm_mhz, sm_max_mhz, [active reason names])
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id torch reports
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        h = hi
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml, self._h, self.source = pynvml, h, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._h
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        self.samples.append((sm, mx, [k for k, b in bits.items() if r & b]))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.samples.append((float(parts[0]), float(parts[1]),
+                                 [n for i, n in enumerate(self.NAMES) if parts[2 + i].lower().startswith("active")]))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self._stop.wait(0.02)
+                if self._nvml is not None:
+                    self._nvml, self.source = None, "nvidia-smi"   # fall back for the remaining samples
+            self._stop.wait(0.005 if self._nvml is not None else 0.02)
 
     def __enter__(self):
         self._t.start()
@@ -102,12 +141,11 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = [n for n in self.NAMES if any(n in s[2] for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": reasons,
+                "samples": len(self.samples), "source": self.source}
 
 
 def make_modules(workload, variant):
