@@ -293,6 +293,40 @@ __global__ void __launch_bounds__(kFftThreads) fe_fft_kernel(fe_fft_args a) {
 template <int E>
 __host__ __device__ constexpr int fe_rfft_zunits() { return 33 * E; }   // transpose buffer A[k2*33 + n1]; Z (32*E) reuses it
 
+// Filterbank phase of fe_rfft_kernel for FT frames per CTA (stride FT + 1 is a compile-time constant: the band
+// loop's shared-memory loads take immediate offsets).  lane -> (filter slot sub, frame tl); weights in shared memory.
+template <int FT>
+__device__ __forceinline__ void fe_rfft_fbank(int warp, int lane, int n_filter, const int4* __restrict__ s_band,
+                                              const float* __restrict__ s_bw, const float* __restrict__ s_pw,
+                                              float* __restrict__ s_tile) {
+  constexpr int ST = FT + 1, FPW = 32 / FT;
+  const int tl = lane & (FT - 1), sub = lane / FT;
+  for (int f = warp * FPW + sub; f < n_filter; f += kFftWarps * FPW) {
+    const int4 band = s_band[f];
+    const int len = band.y;
+    const float* pcol = s_pw + band.x * ST + tl;
+    const float* w = s_bw + band.z;
+    float acc = 0.0f;                                               // same summation order as fe_fbank_apply
+    int i = 0;
+#pragma unroll 1
+    for (; i + 4 <= len; i += 4, pcol += 4 * ST, w += 4) {
+      const float p0 = pcol[0], p1 = pcol[ST], p2 = pcol[2 * ST], p3 = pcol[3 * ST];
+      const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+      acc = fmaf(p0, w0, acc);
+      acc = fmaf(p1, w1, acc);
+      acc = fmaf(p2, w2, acc);
+      acc = fmaf(p3, w3, acc);
+    }
+    const int rem = len - i;                                        // 0..3, all loads before the FMAs
+    const float p0 = rem > 0 ? pcol[0] : 0.0f, p1 = rem > 1 ? pcol[ST] : 0.0f, p2 = rem > 2 ? pcol[2 * ST] : 0.0f;
+    const float w0 = rem > 0 ? w[0] : 0.0f, w1 = rem > 1 ? w[1] : 0.0f, w2 = rem > 2 ? w[2] : 0.0f;
+    if (rem > 0) acc = fmaf(p0, w0, acc);
+    if (rem > 1) acc = fmaf(p1, w1, acc);
+    if (rem > 2) acc = fmaf(p2, w2, acc);
+    s_tile[f * ST + tl] = acc;
+  }
+}
+
 template <int MODE, int E>
 __global__ void __launch_bounds__(kFftThreads, E == 16 ? 2 : 4) fe_rfft_kernel(fe_fft_args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -415,26 +449,18 @@ __global__ void __launch_bounds__(kFftThreads, E == 16 ? 2 : 4) fe_rfft_kernel(f
   const float* tile_src = s_pw;
   int n_ch = NFREQ;
   if (MODE == 1) {
-    for (int f = warp * fpw + sub; f < a.n_filter; f += kFftWarps * fpw) {
-      const int4 band = s_band[f];
-      const int s0 = band.x, len = band.y;
-      const float* pcol = s_pw + s0 * stride + tl;
-      float acc = 0.0f;                                               // same summation order as fe_fbank_apply
-      if (bw_shared) {
-        const float* w = s_bw + band.z;
-        int i = 0;
-        for (; i + 4 <= len; i += 4) {
-          acc = fmaf(pcol[(i + 0) * stride], w[i + 0], acc);
-          acc = fmaf(pcol[(i + 1) * stride], w[i + 1], acc);
-          acc = fmaf(pcol[(i + 2) * stride], w[i + 2], acc);
-          acc = fmaf(pcol[(i + 3) * stride], w[i + 3], acc);
-        }
-        for (; i < len; ++i) acc = fmaf(pcol[i * stride], w[i], acc);
-      } else {
+    if (bw_shared) {
+      if (ft == 16) fe_rfft_fbank<16>(warp, lane, a.n_filter, s_band, s_bw, s_pw, s_tile);
+      else fe_rfft_fbank<32>(warp, lane, a.n_filter, s_band, s_bw, s_pw, s_tile);
+    } else {   // a bank denser than any triangular one: weights stay in global memory
+      for (int f = warp * fpw + sub; f < a.n_filter; f += kFftWarps * fpw) {
+        const int4 band = s_band[f];
+        const float* pcol = s_pw + band.x * stride + tl;
         const float* w = gbw + band.z;
-        for (int i = 0; i < len; ++i) acc = fmaf(pcol[i * stride], __ldg(w + i), acc);
+        float acc = 0.0f;
+        for (int i = 0; i < band.y; ++i) acc = fmaf(pcol[i * stride], __ldg(w + i), acc);
+        s_tile[f * stride + tl] = acc;
       }
-      s_tile[f * stride + tl] = acc;
     }
     __syncthreads();
     tile_src = s_tile;
