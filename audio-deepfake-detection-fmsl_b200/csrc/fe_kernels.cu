@@ -150,8 +150,8 @@ __device__ __forceinline__ void fe_warp_rfft_power(int lane, const float* __rest
     const fe_c2 r = s_rtw[k];
     const float tx = r.x * ox - r.y * oy, ty = r.x * oy + r.y * ox;
     const float px = ex + tx, py = ey + ty, mx = ex - tx, my = ey - ty;
-    pw[(size_t)k * pw_stride] = 0.25f * (px * px + py * py);
-    pw[(size_t)(NH - k) * pw_stride] = 0.25f * (mx * mx + my * my);
+    pw[k * pw_stride] = px * px + py * py;                 // s_win carries the factor 1/2: no 1/4 here
+    pw[(NH - k) * pw_stride] = mx * mx + my * my;
   }
 }
 
@@ -359,7 +359,11 @@ __global__ void __launch_bounds__(kFftThreads, E == 16 ? 2 : 4) fe_rfft_kernel(f
   // ---- constants -> shared, frame-independent twiddles -> registers ------------------------------
   {
     const float4* gw = reinterpret_cast<const float4*>(blob + h->off_window);
-    for (int i = tid; i < NFFT / 4; i += kFftThreads) reinterpret_cast<float4*>(s_win)[i] = gw[i];
+    // the window is stored halved: Z comes out halved and the split's 1/4 on |X|^2 disappears (exact: power of two)
+    for (int i = tid; i < NFFT / 4; i += kFftThreads) {
+      const float4 w = gw[i];
+      reinterpret_cast<float4*>(s_win)[i] = make_float4(0.5f * w.x, 0.5f * w.y, 0.5f * w.z, 0.5f * w.w);
+    }
     const fe_c2* gr = reinterpret_cast<const fe_c2*>(blob + h->off_rtwiddle);
     for (int i = tid; i <= NH / 2; i += kFftThreads) s_rtw[i] = gr[i];
   }
