@@ -61,6 +61,20 @@ def test_sweep_labels_and_blocks_are_world_size_independent(fe):
     assert sum(hi - lo for lo, hi in spans) == 71237
 
 
+def test_sweep_blocks_are_deterministic_and_class_dependent(fe):
+    from importlib import import_module
+    sweep = import_module("audio-deepfake-detection-fmsl_b200.sweep")
+    cpu = torch.device("cpu")
+    a = sweep.synthetic_block(3, cpu, n_total=4000, n_bonafide=3100)
+    b = sweep.synthetic_block(3, cpu, n_total=4000, n_bonafide=3100)
+    assert a.shape == (4000 - 3 * 1024, 64600) and torch.equal(a, b)       # the last block is short
+    assert not torch.equal(a[:10], sweep.synthetic_block(2, cpu, n_total=4000, n_bonafide=3100)[:10])
+    assert float(a.abs().max()) <= 1.0 * float(torch.exp(torch.tensor(0.35 * 6)))
+    # utterances 3072..3099 are bonafide (median gain 0.7), the rest spoofed (median gain 1.0)
+    rms = a.pow(2).mean(dim=1).sqrt()
+    assert float(rms[:28].median()) < float(rms[28:].median())
+
+
 # ---- GPU: the CUDA front-end in the slot ------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("key,fmsl", [("maze5", False), ("maze5_fmsl", True)])
