@@ -556,7 +556,6 @@ __global__ void __launch_bounds__(kTailThreads) fe_tail_kernel(fe_tail_args a) {
 // Only the delta stencils go through shared memory.  grid (tiles, rows), block = tt + 2*halo rounded up to a warp.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastMax = 32;
-constexpr int kTailBatch = 10;   // energies fetched per batch (all loads in flight together)
 
 __device__ __forceinline__ float fast_log_energy(float v, int log_mode, float floor_db) {
   if (log_mode == B200FE_LOG_DB) {
@@ -592,6 +591,7 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
   float* s_c = reinterpret_cast<float*>(smem_raw);      // [nc][w]
   float* s_d = s_c + nc * w;                            // [nc][w]
   float* s_dct = s_d + nc * w;                          // [nfil][4*KQ] (zero padded rows)
+  float* s_e = s_dct + nfil * kRegs;                    // [nfil][w] energies, fetched asynchronously
 
   const int j = threadIdx.x;
   const int64_t row_local = blockIdx.y;
@@ -599,6 +599,16 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
   const int t0 = blockIdx.x * tt;
   const int nF = a.n_frames;
   const int tv0 = t0 - halo;
+  const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;   // tile position of this position's (clamped) frame
+  // the frame's energies come from L2 (several hundred cycles): start all the fetches now (cp.async, no registers
+  // held), behind the table and group-maximum loads below; each thread later reads only what it fetched itself
+  if (j < w) {
+    const float* src = a.energies + (size_t)row_local * nfil * nF + (tv0 + tcl);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_e + j);
+    for (int f = 0; f < nfil; ++f)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(f * w) * 4u), "l"(src + (size_t)f * nF) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
   if (ncoef > 0) {
@@ -613,46 +623,35 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
     const float gmax = __uint_as_float(a.group_max[row / a.top_db_group]);
     floor_db = 3.0102999566398120f * __log2f(fmaxf(gmax, 1e-10f)) - a.top_db;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;   // tile position of this position's (clamped) frame
   const bool owner = j >= halo && j < halo + tt && (t0 + j - halo) < nF;   // this thread stores frame t0 + j - halo
   float* out_p = a.out + (size_t)row * a.n_out * nF + (t0 + j - halo);    // walks down the channels
   float c[kRegs];
 #pragma unroll
   for (int k = 0; k < kRegs; ++k) c[k] = 0.0f;
   if (j < w) {
-    const float* src = a.energies + (size_t)row_local * nfil * nF + (tv0 + tcl);
+    const float* ej = s_e + j;
     if (ncoef > 0) {
       const float4* dr = reinterpret_cast<const float4*>(s_dct);
-      // the frame's energies come from L2 (~300 cycles): fetch them kTailBatch at a time, all loads in flight together
-#pragma unroll 1
-      for (int f0 = 0; f0 < nfil; f0 += kTailBatch) {
-        float e[kTailBatch];
+#pragma unroll 4
+      for (int f = 0; f < nfil; ++f, dr += KQ) {
+        const float v = fast_log_energy(ej[f * w], a.log_mode, floor_db);
 #pragma unroll
-        for (int u = 0; u < kTailBatch; ++u) e[u] = (f0 + u < nfil) ? __ldg(src + (size_t)u * nF) : 0.0f;
-        src += (size_t)kTailBatch * nF;
-#pragma unroll
-        for (int u = 0; u < kTailBatch; ++u) {
-          if (f0 + u < nfil) {
-            const float v = fast_log_energy(e[u], a.log_mode, floor_db);
-#pragma unroll
-            for (int k4 = 0; k4 < KQ; ++k4) {
-              const float4 d = dr[k4];
-              c[4 * k4 + 0] = fmaf(v, d.x, c[4 * k4 + 0]);
-              c[4 * k4 + 1] = fmaf(v, d.y, c[4 * k4 + 1]);
-              c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
-              c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
-            }
-          }
-          dr += KQ;
+        for (int k4 = 0; k4 < KQ; ++k4) {
+          const float4 d = dr[k4];
+          c[4 * k4 + 0] = fmaf(v, d.x, c[4 * k4 + 0]);
+          c[4 * k4 + 1] = fmaf(v, d.y, c[4 * k4 + 1]);
+          c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
+          c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
         }
       }
     } else {
       // no DCT: channel k is the (log) energy of filter k
 #pragma unroll
       for (int k = 0; k < kRegs; ++k)
-        if (EXACT || k < nc) c[k] = fast_log_energy(__ldg(src + (size_t)k * nF), a.log_mode, floor_db);
+        if (EXACT || k < nc) c[k] = fast_log_energy(ej[k * w], a.log_mode, floor_db);
     }
     if (a.deltas >= 1) {
       float* sc = s_c + j;
@@ -940,7 +939,7 @@ static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cuda
   const int threads = (w + 31) & ~31;
   const int nc = a.n_coef > 0 ? a.n_coef : a.n_filter;
   const int kq = (nc + 3) / 4;
-  const size_t smem = ((size_t)2 * nc * w + (size_t)a.n_filter * 4 * kq) * 4;
+  const size_t smem = ((size_t)2 * nc * w + (size_t)a.n_filter * 4 * kq + (size_t)a.n_filter * w) * 4;
   typedef void (*kern_t)(fe_tail_args);
   const int n = a.deltas > 0 ? (a.delta_win - 1) / 2 : 0;
   const bool exact = nc == 4 * kq;
