@@ -473,3 +473,19 @@ def test_ragged_tiny_and_long_clips(fe):
         # the constant clip sits on the top_db floor almost everywhere: compare where the reference is above it
         a, b = out.cpu().numpy()[0], ref[0]
         assert np.isfinite(a).all() and np.abs(a[0] - b[0]).max() <= 1e-3 * max(1.0, np.abs(b[0]).max())
+
+
+def test_tail_with_a_matrix_that_is_not_a_dct(fe):
+    """The C-ABI takes the coefficient matrix as a table: an arbitrary one must go through the unfolded path."""
+    torch.manual_seed(1)
+    mat = torch.randn(20, 20)
+    fb = fe.linear_fbanks(257, 0.0, 8000.0, 20, 16000)
+    kw = dict(n_fft=512, win_length=320, hop_length=160, window=torch.hann_window(320), fbank=fb,
+              log_mode=fe._lib.LOG_DB, top_db=80.0)
+    x = cuda(synth.s1_noise(3))
+    out = fe.FrontEndEngine(dct=mat, **kw).features(x).cpu()
+    # same energies through the DCT-free path (log filterbank energies), then the matrix on the host
+    logfb = fe.FrontEndEngine(dct=None, **kw).features(x).cpu()
+    ref = torch.einsum("rft,fk->rkt", logfb.double(), mat.double()).float()
+    assert out.shape == ref.shape == (3, 20, 404)
+    assert float((out - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
