@@ -385,6 +385,19 @@ def main():
         roofline["tensor_view"] = {"executed_flops_per_utt": W["n_frames"] * flops_per_frame, "achieved": tf, "peak": tpeak,
                                    "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": tsrc,
                                    "dense_dft_flops_per_utt": 2 * W["n_frames"] * win * (n_fft + 2)}
+    if variant == "fft":
+        # the FFT variant's arithmetic intensity is above the fp32 ridge, so the fp32-ALU view shows
+        # the limiter.  Algorithmic flops per frame: 5 N log2 N for the N = n_fft/2 point complex FFT, 10 N for the
+        # real-FFT split and the powers, 2 per non-zero filterbank weight (~2 per bin for a triangular bank).
+        n_fft = 1024 if args.workload == "mel" else 512
+        n = n_fft // 2
+        flops_per_frame = 5 * n * (n.bit_length() - 1) + 10 * n + 4 * (n + 1)
+        props = torch.cuda.get_device_properties(dev)
+        peak32 = props.multi_processor_count * 128 * 2 * (clocks.summary().get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        tf = B * W["n_frames"] * flops_per_frame / (dom_ms / 1000.0) / 1e12
+        roofline["fp32_view"] = {"algorithmic_flops_per_utt": W["n_frames"] * flops_per_frame, "achieved": tf,
+                                 "peak": peak32, "unit": "TFLOP/s", "frac": tf / peak32,
+                                 "peak_source": "SMs x 128 lanes x 2 (FMA) x max SM clock (nominal)"}
     cpu_baseline = None
     if not args.no_cpu_baseline:
         thr, threads, n = cpu_reference_throughput(args.workload, args.cpu_budget)
