@@ -267,7 +267,7 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
         if (e != cudaSuccess) return cuda_fail(e, "dense-rows kernel launch");
         g_launches += (nr + 65534) / 65535;
         fe_fft_args fs = fa;
-        fs.wave = dense - (size_t)r0 * T;  // fe_stream_launch addresses rows absolutely
+        fs.wave_chunk = dense;
         fs.offsets = nullptr;
         fs.lengths = nullptr;
         e = fe_stream_launch(p, fs, r0, nr, gemm_ws, stream, &launches);

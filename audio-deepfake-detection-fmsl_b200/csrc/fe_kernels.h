@@ -6,6 +6,8 @@
 
 struct fe_fft_args {
   const float* wave;        // dense [R][T] or flat ragged clips
+  const float* wave_chunk;  // streaming kernel only: dense rows of THIS launch ([rows][T], first row = row_base) when the
+                            // input was staged by fe_launch_dense_rows; NULL: rows are read from `wave`
   const int64_t* offsets;   // ragged: start of each row's clip (floats), else NULL
   const int32_t* lengths;   // ragged: clip lengths, else NULL
   const void* tables;       // device blob

@@ -544,7 +544,7 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
                              void* gemm_ws, cudaStream_t stream, int* launches) {
   *launches = 0;
   stream_args a;
-  a.wave = fa.wave + row_base * fa.T;
+  a.wave = fa.wave_chunk ? fa.wave_chunk : fa.wave + row_base * fa.T;
   a.tables = fa.tables;
   a.energies = fa.out;
   a.group_max = fa.group_max;
