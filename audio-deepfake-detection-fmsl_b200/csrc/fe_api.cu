@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 
 #include "fe_common.h"
 #include "fe_gemm.h"
@@ -21,11 +22,12 @@ int32_t cuda_fail(cudaError_t e, const char* what) {
 }
 
 int32_t check_device() {
-  static int cached = 0;  // 0 unknown, 1 ok, -1 bad
-  if (cached == 1) return B200FE_OK;
+  // per device ordinal: a process may drive several GPUs (0 unknown, 1 ok); a failed check is not cached
+  static std::atomic<int> cached[kFeMaxDevices];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) { fe_set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return B200FE_ERR_NO_DEVICE; }
+  if (dev >= 0 && dev < kFeMaxDevices && cached[dev].load(std::memory_order_relaxed) == 1) return B200FE_OK;
   int major = 0;
   e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (e != cudaSuccess) { fe_set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); return B200FE_ERR_NO_DEVICE; }
@@ -33,7 +35,7 @@ int32_t check_device() {
     fe_set_error("device compute capability %d.x: this library is built for sm_100a only", major);
     return B200FE_ERR_NO_DEVICE;
   }
-  cached = 1;
+  if (dev >= 0 && dev < kFeMaxDevices) cached[dev].store(1, std::memory_order_relaxed);
   return B200FE_OK;
 }
 
@@ -340,37 +342,37 @@ extern "C" int32_t b200fe_compute_deltas(const float* in, int64_t rows, int64_t 
 // ---- host-buffer path ---------------------------------------------------------------------------
 namespace {
 struct host_slot_layout {
-  int64_t wave_bytes, out_bytes, ws_bytes, slot_bytes;
+  int64_t pcm_bytes, wave_bytes, out_bytes, ws_bytes, slot_bytes;
 };
-int32_t host_layout(const b200fe_params* p, int64_t chunk_rows, int64_t T, host_slot_layout* L) {
+int32_t host_layout(const b200fe_params* p, int64_t chunk_rows, int64_t T, bool pcm16, host_slot_layout* L) {
   const int64_t nf = b200fe_n_frames(p, T);
   if (nf < 0) return (int32_t)nf;
   const int64_t n_out = b200fe_n_out_channels(p);
   const int64_t ws = b200fe_workspace_bytes(p, chunk_rows, T);
   if (ws < 0) return (int32_t)ws;
+  L->pcm_bytes = pcm16 ? ((chunk_rows * T * 2 + 255) & ~(int64_t)255) : 0;
   L->wave_bytes = (chunk_rows * T * 4 + 255) & ~(int64_t)255;
   L->out_bytes = (chunk_rows * n_out * nf * 4 + 255) & ~(int64_t)255;
   L->ws_bytes = (ws + 255) & ~(int64_t)255;
-  L->slot_bytes = L->wave_bytes + L->out_bytes + L->ws_bytes;
+  L->slot_bytes = L->pcm_bytes + L->wave_bytes + L->out_bytes + L->ws_bytes;
   return B200FE_OK;
 }
-}  // namespace
 
-extern "C" int64_t b200fe_host_staging_bytes(const b200fe_params* p, int64_t chunk_rows, int64_t T, int32_t n_streams) {
+int64_t host_staging_bytes(const b200fe_params* p, int64_t chunk_rows, int64_t T, int32_t n_streams, bool pcm16) {
   if (chunk_rows < 1 || n_streams < 1 || n_streams > 4) {
     fe_set_error("chunk_rows=%lld n_streams=%d out of range", (long long)chunk_rows, n_streams);
     return B200FE_ERR_BAD_ARG;
   }
   host_slot_layout L;
-  int32_t st = host_layout(p, chunk_rows, T, &L);
+  int32_t st = host_layout(p, chunk_rows, T, pcm16, &L);
   if (st != B200FE_OK) return st;
   return L.slot_bytes * n_streams;
 }
 
-extern "C" int32_t b200fe_features_forward_host(const float* wave_host, int64_t R, int64_t T, const b200fe_params* p,
-                                                const void* tables, float* out_host, void* staging,
-                                                size_t staging_bytes, int64_t chunk_rows, void* const* streams,
-                                                int32_t n_streams) {
+// wave_host: float32 rows (pcm16 == false) or int16 PCM rows (pcm16 == true: converted on the device, x / 32768)
+int32_t forward_host(const void* wave_host, bool pcm16, int64_t R, int64_t T, const b200fe_params* p,
+                     const void* tables, float* out_host, void* staging, size_t staging_bytes, int64_t chunk_rows,
+                     void* const* streams, int32_t n_streams) {
   int64_t launches = 0;
   g_launches = 0;
   if (!wave_host || !out_host || !staging || !streams) { fe_set_error("NULL argument"); return B200FE_ERR_BAD_ARG; }
@@ -379,7 +381,7 @@ extern "C" int32_t b200fe_features_forward_host(const float* wave_host, int64_t 
     fe_set_error("the host-buffer path needs top_db_group == 1 (chunks are finished independently)");
     return B200FE_ERR_UNSUPPORTED;
   }
-  const int64_t need = b200fe_host_staging_bytes(p, chunk_rows, T, n_streams);
+  const int64_t need = host_staging_bytes(p, chunk_rows, T, n_streams, pcm16);
   if (need < 0) return (int32_t)need;
   if (staging_bytes < (size_t)need) {
     fe_set_error("staging: %zu bytes given, %lld needed", staging_bytes, (long long)need);
@@ -387,20 +389,29 @@ extern "C" int32_t b200fe_features_forward_host(const float* wave_host, int64_t 
   }
   if (((uintptr_t)staging & 255) != 0) { fe_set_error("staging must be 256-byte aligned"); return B200FE_ERR_ALIGNMENT; }
   host_slot_layout L;
-  host_layout(p, chunk_rows, T, &L);
+  host_layout(p, chunk_rows, T, pcm16, &L);
   const int64_t nf = b200fe_n_frames(p, T);
   const int64_t n_out = b200fe_n_out_channels(p);
+  const size_t in_elt = pcm16 ? 2 : 4;
   int64_t c = 0;
   for (int64_t r0 = 0; r0 < R; r0 += chunk_rows, ++c) {
     const int64_t nr = R - r0 < chunk_rows ? R - r0 : chunk_rows;
     const int s = (int)(c % n_streams);
     cudaStream_t st = (cudaStream_t)streams[s];
     char* slot = (char*)staging + (size_t)s * L.slot_bytes;
-    float* d_wave = (float*)slot;
-    float* d_out = (float*)(slot + L.wave_bytes);
-    void* d_ws = slot + L.wave_bytes + L.out_bytes;
-    cudaError_t e = cudaMemcpyAsync(d_wave, wave_host + (size_t)r0 * T, (size_t)nr * T * 4, cudaMemcpyHostToDevice, st);
+    int16_t* d_pcm = (int16_t*)slot;
+    float* d_wave = (float*)(slot + L.pcm_bytes);
+    float* d_out = (float*)(slot + L.pcm_bytes + L.wave_bytes);
+    void* d_ws = slot + L.pcm_bytes + L.wave_bytes + L.out_bytes;
+    // one copy per chunk and direction
+    cudaError_t e = cudaMemcpyAsync(pcm16 ? (void*)d_pcm : (void*)d_wave, (const char*)wave_host + (size_t)r0 * T * in_elt,
+                                    (size_t)nr * T * in_elt, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+    if (pcm16) {
+      e = fe_launch_i16_rows(d_pcm, d_wave, nr * T, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pcm16 conversion kernel launch");
+      ++launches;
+    }
     int32_t rc = b200fe_features_forward(d_wave, nr, T, nullptr, nullptr, p, tables, d_out, d_ws, (size_t)L.ws_bytes, st);
     if (rc != B200FE_OK) return rc;
     launches += g_launches;
@@ -413,4 +424,27 @@ extern "C" int32_t b200fe_features_forward_host(const float* wave_host, int64_t 
   }
   g_launches = launches;
   return B200FE_OK;
+}
+}  // namespace
+
+extern "C" int64_t b200fe_host_staging_bytes(const b200fe_params* p, int64_t chunk_rows, int64_t T, int32_t n_streams) {
+  return host_staging_bytes(p, chunk_rows, T, n_streams, false);
+}
+
+extern "C" int64_t b200fe_host_staging_bytes_i16(const b200fe_params* p, int64_t chunk_rows, int64_t T, int32_t n_streams) {
+  return host_staging_bytes(p, chunk_rows, T, n_streams, true);
+}
+
+extern "C" int32_t b200fe_features_forward_host(const float* wave_host, int64_t R, int64_t T, const b200fe_params* p,
+                                                const void* tables, float* out_host, void* staging,
+                                                size_t staging_bytes, int64_t chunk_rows, void* const* streams,
+                                                int32_t n_streams) {
+  return forward_host(wave_host, false, R, T, p, tables, out_host, staging, staging_bytes, chunk_rows, streams, n_streams);
+}
+
+extern "C" int32_t b200fe_features_forward_host_i16(const int16_t* pcm_host, int64_t R, int64_t T, const b200fe_params* p,
+                                                    const void* tables, float* out_host, void* staging,
+                                                    size_t staging_bytes, int64_t chunk_rows, void* const* streams,
+                                                    int32_t n_streams) {
+  return forward_host(pcm_host, true, R, T, p, tables, out_host, staging, staging_bytes, chunk_rows, streams, n_streams);
 }

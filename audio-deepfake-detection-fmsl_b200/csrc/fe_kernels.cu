@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
+#include <atomic>
 
 #include "fe_fft.cuh"
 #include "fe_tail.cuh"
@@ -588,10 +589,11 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
   const int tt = a.tt, halo = a.halo, w = tt + 2 * halo;
   const int nfil = a.n_filter, ncoef = a.n_coef;
   const int nc = EXACT ? kRegs : (ncoef > 0 ? ncoef : nfil);
-  float* s_c = reinterpret_cast<float*>(smem_raw);      // [nc][w]
+  float* s_dct = reinterpret_cast<float*>(smem_raw);    // [nfil][4*KQ] (zero padded rows), read as float4: kept first so
+                                                        // that it is 16-byte aligned whatever nc * w is (odd n_coef x odd w)
+  float* s_c = s_dct + nfil * kRegs;                    // [nc][w]
   float* s_d = s_c + nc * w;                            // [nc][w]
-  float* s_dct = s_d + nc * w;                          // [nfil][4*KQ] (zero padded rows)
-  float* s_e = s_dct + nfil * kRegs;                    // [nfil][w] energies, fetched asynchronously
+  float* s_e = s_d + nc * w;                            // [nfil][w] energies, fetched asynchronously
 
   const int j = threadIdx.x;
   const int64_t row_local = blockIdx.y;
@@ -777,6 +779,21 @@ __global__ void __launch_bounds__(256) fe_dense_rows_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// fe_i16_rows_kernel : 16-bit PCM rows -> float32 rows, x / 32768 (exact in fp32: what a FLAC / WAV decoder's
+// float conversion yields, maze5.py:297-351 via librosa / soundfile).  One thread = four samples.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fe_i16_rows_kernel(const int16_t* __restrict__ src, float* __restrict__ dst,
+                                                         int64_t n4, int64_t n) {
+  const float k = 1.0f / 32768.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const short4 v = reinterpret_cast<const short4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = make_float4(k * (float)v.x, k * (float)v.y, k * (float)v.z, k * (float)v.w);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) dst[i] = k * (float)src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // fe_tail_pointwise_kernel : the tail when there is no DCT and no deltas (mel features): out = log/dB(energies)
 // element by element with the arithmetic of fe_tail_load; a row's [n_filter][n_frames] block is contiguous on
 // both sides.  grid (blocks per row, rows), 4 elements per thread, coalesced.
@@ -813,6 +830,23 @@ cudaError_t set_smem(const void* fn, size_t bytes) {
 }
 
 }  // namespace
+
+int fe_current_device(void) {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
+int fe_device_sms(int dev) {
+  static std::atomic<int> cache[kFeMaxDevices];   // 0: not queried yet
+  if (dev >= 0 && dev < kFeMaxDevices) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int sms = 0;
+  if (dev < 0 || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) return 1;
+  if (dev < kFeMaxDevices) cache[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
 
 int fe_fft_warps_for(int n_fft) {
   // per-warp ping-pong buffers: 2 * (n_fft/2 + 1) complex; keep them within ~96 KB
@@ -888,12 +922,7 @@ cudaError_t fe_launch_fft(const fe_fft_args& a_in, int mode, int64_t rows, cudaS
   if (e != cudaSuccess) return e;
   int64_t launch_grid = grid;
   if (E > 0) {   // persistent CTAs: as many as are resident at once
-    static int sms = 0;
-    if (sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = fe_device_sms(fe_current_device());
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFftThreads, smem);
     if (e != cudaSuccess) return e;
@@ -1029,4 +1058,14 @@ cudaError_t fe_launch_dense_rows(const float* wave, const int64_t* offsets, cons
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+cudaError_t fe_launch_i16_rows(const int16_t* src, float* dst, int64_t n, cudaStream_t stream) {
+  // both pointers 8 / 16-byte aligned (staging slots are 256-byte aligned): vector body + scalar tail
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fe_i16_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, n4, n);
+  return cudaGetLastError();
 }

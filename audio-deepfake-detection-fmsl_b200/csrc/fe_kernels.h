@@ -38,6 +38,11 @@ struct fe_tail_args {
   float top_db;
 };
 
+// Per-device facts, cached per device ordinal (a process may drive several GPUs; lock-free, idempotent fills).
+constexpr int kFeMaxDevices = 64;
+int fe_current_device(void);        // cudaGetDevice, -1 on error
+int fe_device_sms(int dev);         // multiprocessor count of `dev`
+
 size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch, int mode);
 int fe_fft_pick_ft(int n_fft, int hop, int n_ch, int mode);   // frames per CTA, 0: does not fit shared memory
 cudaError_t fe_launch_fft(const fe_fft_args& a, int mode, int64_t rows, cudaStream_t stream);
@@ -51,4 +56,6 @@ cudaError_t fe_launch_deltas(const float* in, float* out, int64_t rows, int64_t 
 cudaError_t fe_launch_dense_rows(const float* wave, const int64_t* offsets, const int32_t* lengths,
                                  int64_t row_base, int64_t rows, int64_t T, float preemph, float* dst,
                                  cudaStream_t stream);
+// 16-bit PCM -> float32 (x / 32768), n samples; src 8-byte and dst 16-byte aligned.
+cudaError_t fe_launch_i16_rows(const int16_t* src, float* dst, int64_t n, cudaStream_t stream);
 #endif

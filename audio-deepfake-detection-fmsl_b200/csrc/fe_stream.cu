@@ -23,6 +23,8 @@
 // TMEM holds exactly the four accumulators (4 x 128 columns), so the MMAs of a tile and its drain cannot
 // overlap; everything else does: production runs one stage ahead of the MMAs, the next tile's samples and
 // operand stages are loaded during MMA tail and drain.
+#include <atomic>
+
 #include "fe_tc.cuh"
 
 #include "fe_gemm.cuh"
@@ -138,8 +140,11 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   const int nbuf = h->gemm_nbuf;   // emission buffers of the drain (2 or 4)
   const int rs = hop * 4;        // bytes per hop-block row (dense; the 128-byte swizzle keeps lane <-> frame reads conflict-free)
 
-  if (!h->gemm_ok) {   // tables without the variant's tiles: report instead of computing garbage
-    if (tid == 0) atomicExch(a.error_flag, 98);
+  if (!h->gemm_ok) {
+    // tables without the variant's tiles (a C-ABI caller that set variant = DFT_GEMM without asking
+    // b200fe_tables_variant): the launch must not look successful -> error flag + trap, surfaced to the caller as
+    // B200FE_ERR_CUDA by the next CUDA call, like a protocol timeout
+    if (tid == 0) mbar_timeout(a.error_flag, 98);
     return;
   }
   unsigned char* s_samp = smem + L.samp;
@@ -589,15 +594,18 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
   }
   const int smem = make_layout(a.hop, a.nhalf, a.kpairs).total;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-  static int attr_done = 0;
-  if (attr_done < smem) {
-    cudaError_t e = cudaFuncSetAttribute(fe_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_done = smem;
+  const int dev = fe_current_device();
+  if (dev < 0) return cudaErrorInvalidDevice;
+  {
+    // the opt-in is per device (context): remembered per device ordinal, largest size granted so far
+    static std::atomic<int> attr_done[kFeMaxDevices];
+    if (dev >= kFeMaxDevices || attr_done[dev].load(std::memory_order_relaxed) < smem) {
+      cudaError_t e = cudaFuncSetAttribute(fe_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      if (dev < kFeMaxDevices) attr_done[dev].store(smem, std::memory_order_relaxed);
+    }
   }
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = fe_device_sms(dev);
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
 #ifdef FE_GEMM_TRACE
   cudaError_t e = cudaMemsetAsync(a.error_flag, 0, 65536, stream);

@@ -90,7 +90,12 @@ def run_sweep(frontend: nn.Module, scorer: nn.Module, device: torch.device, *, n
     for a, b, c in timed:
         fe_ms += a.elapsed_time(b)
         cls_ms += b.elapsed_time(c)
-    full = gather_scores(local, n_total, group)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    full = gather_scores(local, n_total, group)      # the one collective of the path, timed alone
+    g1.record()
+    torch.cuda.synchronize(device)
+    gather_ms = g0.elapsed_time(g1)
     scores = full.cpu().numpy()
     checks = gather_scores(local_ck, n_total, group).cpu().numpy()
     wall = time.perf_counter() - t0
@@ -98,4 +103,4 @@ def run_sweep(frontend: nn.Module, scorer: nn.Module, device: torch.device, *, n
     return dict(n_total=n_total, n_local=hi - lo, eer=eer, min_dcf=dcf, eer_threshold=thr,
                 scores_sha256=hashlib.sha256(scores.astype("<f4").tobytes()).hexdigest(),
                 features_sha256=hashlib.sha256(checks.astype("<i8").tobytes()).hexdigest(),
-                frontend_ms=fe_ms, classifier_ms=cls_ms, wall_s=wall, scores=scores)
+                frontend_ms=fe_ms, classifier_ms=cls_ms, gather_ms=gather_ms, wall_s=wall, scores=scores)

@@ -219,28 +219,52 @@ class FrontEndEngine:
                                                            out.data_ptr(), C.c_void_p(stream)))
         return out
 
+    def _params_for_call(self, p: _lib.Params, T: int, data_ptr: Optional[int], staged: bool) -> _lib.Params:
+        """AUTO's per-call fallback, shared by every entry point: the streaming tcgen05 kernel fetches rows with
+        TMA boxes, which need ``T % 4 == 0`` and (unless the rows are staged into the workspace first: ragged or
+        pre-emphasised input) a 16-byte aligned waveform.  AUTO switches to the FFT variant for such a call; an
+        explicit variant request does not (the library then reports "unsupported")."""
+        if p.variant != _lib.VARIANT_DFT_GEMM or self.requested_variant != "auto":
+            return p
+        staged = staged or p.preemph != 0.0
+        if T % 4 != 0 or (not staged and data_ptr is not None and data_ptr % 16 != 0):
+            p = _lib.Params.from_buffer_copy(p)
+            p.variant = _lib.VARIANT_FFT
+        return p
+
     def features(self, wave2d: Tensor, group: int = 1, out: Optional[Tensor] = None,
                  offsets: Optional[Tensor] = None, lengths: Optional[Tensor] = None,
-                 T: Optional[int] = None) -> Tensor:
+                 T: Optional[int] = None, validate: bool = True) -> Tensor:
         """``wave2d`` is ``(R,T)`` contiguous, or — with ``offsets``/``lengths``/``T`` — the flat
-        ragged clip buffer.  Returns ``(R, n_out, n_frames)``."""
+        ragged clip buffer.  Returns ``(R, n_out, n_frames)``.  ``validate`` (ragged input only) checks the
+        clip table on the device first — every clip non-empty and inside the flat buffer, as the
+        reference's ``pad()`` would raise on an empty clip (maze5.py:280-285); it costs one host
+        synchronisation per call and can be switched off by callers that built the table themselves."""
         self._check_wave(wave2d)
         dev = wave2d.device
         if offsets is None:
+            if lengths is not None:
+                raise ValueError("lengths given without offsets")
             R, T = wave2d.shape
         else:
+            if lengths is None or T is None:
+                raise ValueError("ragged input needs offsets, lengths and T")
             R = offsets.numel()
             if offsets.dtype != torch.int64 or lengths.dtype != torch.int32:
                 raise TypeError("offsets must be int64 and lengths int32")
             if offsets.device != dev or lengths.device != dev:
                 raise ValueError("offsets / lengths must be on the waveform's device")
-        p = self._params_with_group(group)
-        if (p.variant == _lib.VARIANT_DFT_GEMM and self.requested_variant == "auto"
-                and (T % 4 != 0 or (offsets is None and p.preemph == 0.0 and wave2d.data_ptr() % 16 != 0))):
-            # the streaming kernel's TMA boxes need 16-byte aligned rows; AUTO may switch, an explicit
-            # variant request may not (the library then reports "unsupported")
-            p = _lib.Params.from_buffer_copy(p)
-            p.variant = _lib.VARIANT_FFT
+            if lengths.numel() != R or R < 1:
+                raise ValueError("offsets and lengths must have the same, non-zero number of entries")
+            if validate:
+                l64 = lengths.to(torch.int64)
+                bad = torch.stack([(l64 < 1).any(), (offsets < 0).any(), ((offsets + l64) > wave2d.numel()).any()])
+                bad = bad.tolist()
+                if bad[0]:
+                    raise ValueError("ragged input: every clip must have at least one sample")
+                if bad[1] or bad[2]:
+                    raise ValueError("ragged input: a clip lies outside the flat buffer")
+        p = self._params_for_call(self._params_with_group(group), T, wave2d.data_ptr(), offsets is not None)
         nf = self.n_frames(T)
         if out is None:
             out = torch.empty((R, self.n_out, nf), dtype=torch.float32, device=dev)
@@ -265,22 +289,24 @@ class FrontEndEngine:
         nf = self.n_frames(T)
         if out is None:
             out = torch.empty((R, self.params.n_filter, nf), dtype=torch.float32, device=dev)
-        ws_bytes = _lib.check(self.lib.b200fe_workspace_bytes(C.byref(self.params), R, T))
+        p = self._params_for_call(self.params, T, wave2d.data_ptr(), False)
+        ws_bytes = _lib.check(self.lib.b200fe_workspace_bytes(C.byref(p), R, T))
         ws = self.workspace_on(dev, ws_bytes)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(self.lib.b200fe_fbank_energies_forward(
-                wave2d.data_ptr(), R, T, None, None, C.byref(self.params), self.tables_on(dev).data_ptr(),
+                wave2d.data_ptr(), R, T, None, None, C.byref(p), self.tables_on(dev).data_ptr(),
                 out.data_ptr(), ws.data_ptr(), ws.numel(), C.c_void_p(stream)))
         return out
 
     def features_host(self, wave_host: Tensor, out_host: Optional[Tensor] = None, *, device=None,
                       chunk_rows: int = 512, n_streams: int = 3) -> Tensor:
-        """End-to-end path: HOST ``(R,T)`` float32 (ideally pinned) in, HOST features out, with the
-        host<->device copies pipelined against the kernels inside the library
-        (``b200fe_features_forward_host``)."""
-        if wave_host.device.type != "cpu" or wave_host.dtype != torch.float32 or wave_host.dim() != 2:
-            raise TypeError("features_host expects a 2-D float32 CPU tensor")
+        """End-to-end path: HOST ``(R,T)`` float32 — or int16 PCM, converted ``x / 32768`` on the device so that only
+        half the bytes cross PCIe — (ideally pinned) in, HOST features out, with the host<->device copies
+        pipelined against the kernels inside the library (``b200fe_features_forward_host[_i16]``)."""
+        if wave_host.device.type != "cpu" or wave_host.dtype not in (torch.float32, torch.int16) or wave_host.dim() != 2:
+            raise TypeError("features_host expects a 2-D float32 (or int16 PCM) CPU tensor")
+        pcm16 = wave_host.dtype == torch.int16
         wave_host = wave_host.contiguous()
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         R, T = wave_host.shape
@@ -289,7 +315,9 @@ class FrontEndEngine:
             out_host = torch.empty((R, self.n_out, nf), dtype=torch.float32, pin_memory=True)
         chunk_rows = max(1, min(int(chunk_rows), R))
         n_streams = max(1, min(int(n_streams), 4))
-        need = _lib.check(self.lib.b200fe_host_staging_bytes(C.byref(self.params), chunk_rows, T, n_streams))
+        p = self._params_for_call(self.params, T, None, False)   # staged rows are 256-byte aligned
+        sizer = self.lib.b200fe_host_staging_bytes_i16 if pcm16 else self.lib.b200fe_host_staging_bytes
+        need = _lib.check(sizer(C.byref(p), chunk_rows, T, n_streams))
         key = ("host", device)
         st = self._workspace.get(key)
         if st is None or st.numel() < need:
@@ -304,8 +332,9 @@ class FrontEndEngine:
         with torch.cuda.device(device):
             tables = self.tables_on(device)
             torch.cuda.current_stream(device).synchronize()  # tables upload finished
-            _lib.check(self.lib.b200fe_features_forward_host(
-                wave_host.data_ptr(), R, T, C.byref(self.params), tables.data_ptr(), out_host.data_ptr(),
+            call = self.lib.b200fe_features_forward_host_i16 if pcm16 else self.lib.b200fe_features_forward_host
+            _lib.check(call(
+                wave_host.data_ptr(), R, T, C.byref(p), tables.data_ptr(), out_host.data_ptr(),
                 st.data_ptr(), st.numel(), chunk_rows, arr, n_streams))
         return out_host
 
@@ -366,11 +395,12 @@ class _Base(nn.Module):
         out = self.engine.features(w, group=self._group_for(shape))
         return out.reshape(shape[:-1] + out.shape[-2:])
 
-    def forward_ragged(self, flat: Tensor, offsets: Tensor, lengths: Tensor, max_len: int = 64600) -> Tensor:
+    def forward_ragged(self, flat: Tensor, offsets: Tensor, lengths: Tensor, max_len: int = 64600,
+                       validate: bool = True) -> Tensor:
         """Config-5 entry: ``flat`` holds variable-length clips back to back; clip ``r`` is
         ``flat[offsets[r] : offsets[r] + lengths[r]]`` and is repeat-padded / truncated to ``max_len``
         inside the loader exactly like ``pad()`` (maze5.py:280-285).  Returns ``(R, C, n_frames)``."""
-        return self.engine.features(flat, group=1, offsets=offsets, lengths=lengths, T=int(max_len))
+        return self.engine.features(flat, group=1, offsets=offsets, lengths=lengths, T=int(max_len), validate=validate)
 
     def forward_host(self, wave_host: Tensor, out_host: Optional[Tensor] = None, **kw) -> Tensor:
         """Host in / host out with pipelined copies (see ``FrontEndEngine.features_host``)."""

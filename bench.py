@@ -23,8 +23,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 UTT_LEN = 64600
-NCU_DRAM_BYTES_PER_UTT_STREAM = 287700  # fe_stream_kernel: (307.0 MB read + 33.65 MB written) / 1184 utterances
-NCU_DRAM_BYTES_PER_UTT_RFFT_MEL = 303500  # fe_rfft_kernel<1,16>: (145.8 MB read + 25.0 MB written) / 563 utterances
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_traffic.json")   # written by tools/ncu_summary.py from ncu --set full captures
 SEED = 1234  # the reference's default seed (maze5.py:449)
 
 WORKLOADS = {
@@ -57,6 +56,18 @@ def read_peaks():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def read_traffic(kernel_key):
+    """DRAM bytes per utterance of the dominant kernel, from the ncu --set full capture of the committed build
+    (profiles/r2_traffic.json: {kernel: {dram_bytes_per_utt, utterances, commit, source}}); None when the kernel
+    has not been captured since it last changed."""
+    try:
+        with open(TRAFFIC_FILE) as fh:
+            rec = json.load(fh).get(kernel_key)
+        return (float(rec["dram_bytes_per_utt"]), f"{rec.get('source')} (commit {rec.get('commit')}, {rec.get('utterances')} utterances)") if rec else (None, None)
+    except Exception:
+        return None, None
 
 
 def read_tensor_peak():
@@ -166,8 +177,12 @@ def cpu_reference_throughput(workload, budget_s, batch=64, max_batches=10_000, t
     B=64 chunks of S1 noise as BASELINE.md section 3 prescribes; returns (utt/s, threads, n_utts)."""
     import torch
     from oracle import synth
-    if threads:
-        torch.set_num_threads(threads)
+    threads = threads or os.cpu_count() or 1     # all host cores, whatever OMP_NUM_THREADS torchrun exported
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except Exception:
+        pass
+    torch.set_num_threads(threads)
     ref = make_reference(workload)
     x = torch.from_numpy(synth.s1_noise(batch, UTT_LEN, seed=SEED))
     ref(x)  # warm-up
@@ -218,6 +233,39 @@ def run_reference_arm(args):
     return 0
 
 
+def config4_record(frontend, dev, rank, world):
+    """BASELINE config 4 inside the bench line: 71,237 synthetic utterances sharded contiguously over the ranks
+    (strong scaling), front-end device-timed per rank (max over ranks), the maze5 classifier behind it, ONE
+    all_gather of the per-utterance scores timed alone, EER on every rank (Maze5_eval.py:588-594)."""
+    import torch
+    import torch.distributed as dist
+    import b200_frontend as fe
+    from importlib import import_module
+    sweep = import_module("audio-deepfake-detection-fmsl_b200.sweep")
+    scorer = fe.MazeScorer(fe.LFCC_FILTS, fmsl=False)
+    fe.fill_deterministic(scorer, sweep.SEED)
+    scorer.to(dev)
+    warm = sweep.synthetic_block(0, dev)
+    for _ in range(2):
+        scorer(frontend(warm))
+    del warm
+    if world > 1:
+        dist.barrier()
+    r = sweep.run_sweep(frontend, scorer, dev, rank=rank, world_size=world)
+    t = torch.tensor([r["frontend_ms"], r["classifier_ms"], r["gather_ms"], r["wall_s"] * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fe_ms, cls_ms, g_ms, wall_ms = t.tolist()
+    return {"workload": f"{r['n_total']} synthetic utterances ({sweep.N_BONAFIDE} bonafide), contiguous shards over {world} rank(s)",
+            "scaling": "strong", "n_gpus": world,
+            "frontend_ms": fe_ms, "frontend_utt_per_s": r["n_total"] / (fe_ms * 1e-3),
+            "classifier_ms": cls_ms, "frontend_plus_classifier_utt_per_s": r["n_total"] / ((fe_ms + cls_ms) * 1e-3),
+            "score_gather_us": g_ms * 1e3, "score_gather": "one all_gather_into_tensor of float32[ceil(N/W)] per rank (NCCL)" if world > 1 else "single rank: no collective",
+            "wall_ms": wall_ms, "eer": r["eer"], "min_dcf": r["min_dcf"], "eer_threshold": r["eer_threshold"],
+            "features_sha256": r["features_sha256"],
+            "timing": "CUDA events per batch summed per rank, max over ranks; gather timed alone with CUDA events"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,6 +277,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -273,7 +322,7 @@ def main():
 
         def step(i):
             j = i % n_sets
-            eng.features(waves[j], out=outs[j], offsets=offsets[j], lengths=lengths[j], T=UTT_LEN)
+            eng.features(waves[j], out=outs[j], offsets=offsets[j], lengths=lengths[j], T=UTT_LEN, validate=False)
     else:
         waves = [(0.1 * torch.randn(B, UTT_LEN, device=dev, generator=gen)).clamp_(-1.0, 1.0) for _ in range(n_sets)]
 
@@ -321,27 +370,83 @@ def main():
     value = world * B * K / (elapsed_ms / 1000.0)
 
     # ---- end to end through host buffers (pinned), copies inside the timed region ----
+    # Headline e2e: 16-bit PCM rows on the host (what the reference's loader decodes FLAC to before its float
+    # conversion, maze5.py:297-351) -> b200fe_features_forward_host_i16 -> float32 features on the host.  The same
+    # with float32 rows on the host is reported beside it (`f32_in`).  One pinned-copy peak per direction is
+    # measured in the same run so that the e2e number has a roofline of its own (`pcie_view`).
     e2e = None
     if not args.no_e2e:
         Be = B
+        if world > 1:   # ranks share the host: pin each rank's threads to its own slice of the cores
+            try:
+                nc = os.cpu_count() or 1
+                per = max(1, nc // world)
+                os.sched_setaffinity(0, range(local_rank * per, min(nc, (local_rank + 1) * per)))
+            except Exception:
+                pass
         xh = torch.empty(Be, UTT_LEN, dtype=torch.float32, pin_memory=True)
         xh.copy_(waves[0][:Be])
+        xi = torch.empty(Be, UTT_LEN, dtype=torch.int16, pin_memory=True)
+        xi.copy_((waves[0][:Be] * 32767.0).round().to(torch.int16))
         oh = torch.empty(Be, W["n_out"], W["n_frames"], dtype=torch.float32, pin_memory=True)
         ke = max(2, min(K, 5))
-        mod.forward_host(xh, oh, chunk_rows=256, n_streams=3)
+
+        def timed_host(xin):
+            mod.forward_host(xin, oh, chunk_rows=256, n_streams=3)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                mod.forward_host(xin, oh, chunk_rows=256, n_streams=3)  # blocks until the features are on the host
+            el = time.perf_counter() - t0
+            te = torch.tensor([el], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return world * Be * ke / float(te.item())
+
+        v_i16 = timed_host(xi)
+        v_f32 = timed_host(xh)
+
+        # pinned-copy peaks of this rank, all ranks copying at once (the N-GPU limiter is the shared host side)
+        def copy_peak(dst, src):
+            best = 0.0
+            for _ in range(3):
+                if world > 1:
+                    dist.barrier()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                dst.copy_(src, non_blocking=True)
+                c1.record()
+                torch.cuda.synchronize()
+                best = max(best, src.numel() * src.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+            return best
+        dbuf = torch.empty_like(waves[0][:Be])
+        h2d_peak = copy_peak(dbuf, xh)
+        d2h_peak = copy_peak(xh, dbuf)
+        del dbuf
+        pk = torch.tensor([h2d_peak, d2h_peak], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            mod.forward_host(xh, oh, chunk_rows=256, n_streams=3)  # blocks until the features are on the host
-        el = time.perf_counter() - t0
-        te = torch.tensor([el], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * Be * ke / float(te.item()), "unit": "utterances/s",
-               "h2d_bytes_per_step": Be * UTT_LEN * 4, "d2h_bytes_per_step": Be * W["n_out"] * W["n_frames"] * 4,
-               "steps": ke, "api": "LFCCDelta.forward_host -> b200fe_features_forward_host (pinned host buffers, 3 streams)"}
-        del xh, oh
+            dist.all_reduce(pk, op=dist.ReduceOp.MIN)
+        h2d_i16 = Be * UTT_LEN * 2
+        d2h = Be * W["n_out"] * W["n_frames"] * 4
+        e2e = {"value": v_i16, "unit": "utterances/s",
+               "h2d_bytes_per_step": h2d_i16, "d2h_bytes_per_step": d2h, "steps": ke,
+               "api": "LFCCDelta.forward_host(int16 PCM) -> b200fe_features_forward_host_i16 (pinned host buffers, "
+                      "3 streams, 256-row chunks; x/32768 on the device, features bit-identical to the float32 call)",
+               "f32_in": {"value": v_f32, "h2d_bytes_per_step": Be * UTT_LEN * 4, "d2h_bytes_per_step": d2h,
+                          "api": "forward_host(float32) -> b200fe_features_forward_host"},
+               "pcie_view": {"h2d_gbs_achieved_per_gpu": v_i16 / world * UTT_LEN * 2 / 1e9,
+                             "d2h_gbs_achieved_per_gpu": v_i16 / world * W["n_out"] * W["n_frames"] * 4 / 1e9,
+                             "h2d_gbs_achieved_per_gpu_f32_in": v_f32 / world * UTT_LEN * 4 / 1e9,
+                             "h2d_peak_gbs": float(pk[0]), "d2h_peak_gbs": float(pk[1]),
+                             "peak_source": "pinned 1 GB torch copy_ per direction, best of 3, min over ranks, all ranks copying at once",
+                             "frac_of_h2d_peak_f32_in": v_f32 / world * UTT_LEN * 4 / 1e9 / max(1e-9, float(pk[0]))}}
+        del xh, xi, oh
+
+    # ---- config 4 sub-record: the 71,237-utterance sweep strong-scaled over the ranks + the score gather ----
+    config4 = None
+    if args.workload == "lfcc" and not args.no_config4:
+        config4 = config4_record(mod, dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -351,29 +456,31 @@ def main():
 
     peak, peak_src = read_peaks()
     alg_bytes_step = B * W["bytes_per_utt"]
-    dom_gbs = alg_bytes_step / (dom_ms / 1000.0) / 1e9
     step_gbs = alg_bytes_step / (ms_per_step / 1000.0) / 1e9
-    # DRAM traffic of the dominant kernel per launch, from the ncu --set full capture of the same kernel
-    # (profiles/r1_stream_final_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum over 1184 utterances)
-    traffic = None
-    traffic_src = None
-    if variant == "dft_gemm" and args.workload == "lfcc":
-        traffic = NCU_DRAM_BYTES_PER_UTT_STREAM * B / max(1, int(dom_launches))
-        traffic_src = "profiles/r1_stream_final_summary.txt"
-    elif variant == "fft" and args.workload == "mel":
-        traffic = NCU_DRAM_BYTES_PER_UTT_RFFT_MEL * B / max(1, int(dom_launches))
-        traffic_src = "profiles/r1_rfft_mel_summary.txt"
+    # `frac` is the WHOLE path's algorithmic bytes over the WHOLE step's time.  `dominant_kernel` is the per-kernel
+    # view: that kernel's OWN algorithmic bytes (waveform read + what it writes) over its own time, and its DRAM
+    # traffic per launch as ncu measured it on the committed build.
+    kname = ("fe_dense_rows_kernel + fe_stream_kernel + fe_tail_fast_kernel (whole step)" if ragged else
+             "fe_stream_kernel" if variant == "dft_gemm" else
+             ("fe_rfft_kernel<1,16>" if args.workload == "mel" else "fe_rfft_kernel<1,8>"))
+    kernel_bytes_per_utt = W["bytes_per_utt"] if ragged else UTT_LEN * 4 + eng.params.n_filter * W["n_frames"] * 4
+    traffic_per_utt, traffic_src = (None, None) if ragged else read_traffic(kname)
+    kern_gbs = B * kernel_bytes_per_utt / (dom_ms / 1000.0) / 1e9
     roofline = {
-        "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic,
-        "traffic_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per utterance x utterances per launch ({traffic_src})" if traffic else None,
+        "bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+        "scope": "whole step: algorithmic bytes of the path (waveform read once + features written once) / step time",
+        "traffic": (traffic_per_utt * B / max(1, int(dom_launches))) if traffic_per_utt else None,
+        "traffic_source": (f"dominant kernel, ncu dram__bytes_read.sum + dram__bytes_write.sum per utterance x utterances "
+                           f"per launch: {traffic_src}") if traffic_per_utt else None,
         "peak_source": peak_src,
-        "kernel": ("fe_dense_rows_kernel + fe_stream_kernel + fe_tail_fast_kernel (whole step)" if ragged else
-                   "fe_stream_kernel" if variant == "dft_gemm" else
-                   ("fe_rfft_kernel<1,16>" if args.workload == "mel" else "fe_rfft_kernel<1,8>")),
-        "kernel_ms_per_step": dom_ms, "kernel_launches_per_step": int(dom_launches),
-        "kernel_share_of_step": dom_ms / ms_per_step,
         "algorithmic_bytes_per_utt": W["bytes_per_utt"],
-        "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak,
+        "dominant_kernel": {
+            "kernel": kname, "ms_per_step": dom_ms, "launches_per_step": int(dom_launches),
+            "share_of_step": dom_ms / ms_per_step,
+            "own_algorithmic_bytes_per_utt": kernel_bytes_per_utt,
+            "achieved": kern_gbs, "frac": kern_gbs / peak,
+            "dram_bytes_per_utt_ncu": traffic_per_utt,
+        },
     }
     if variant == "dft_gemm" and not ragged:
         # the tensor-pipe view of the DFT-GEMM variant.  Executed flops: four folded, parity-split
@@ -400,7 +507,7 @@ def main():
                                  "peak_source": "SMs x 128 lanes x 2 (FMA) x max SM clock (nominal)"}
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        thr, threads, n = cpu_reference_throughput(args.workload, args.cpu_budget)
+        thr, threads, n = cpu_reference_throughput(args.workload, args.cpu_budget, threads=os.cpu_count() or 1)
         cpu_baseline = {"value": thr, "unit": "utterances/s", "cores": threads, "kind": "reference",
                         "sample": f"torchaudio {args.workload} path on host, {n} S1 utterances in B=64 chunks, "
                                   f"{threads} threads ({os.cpu_count()} logical cores)"}
@@ -414,7 +521,7 @@ def main():
         "config": {"workload": W["name"], "batch_per_gpu": B, "variant": variant,
                    "l2": f"inputs/outputs rotate over {n_sets} buffer sets of {alg_bytes_step / 1e9:.2f} GB (> 126 MB L2)",
                    "parallelism": f"dp{world} (utterance shards, no collective on the feature path)"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "config4": config4,
         "gpu_launches": int(launches_per_step) * K, "clocks": clocks.summary(),
     }
     print(json.dumps(line))

@@ -52,7 +52,7 @@ typedef enum b200fe_log_mode {
 
 typedef enum b200fe_variant {
   B200FE_VARIANT_AUTO = 0,       /* fastest measured variant that supports the configuration        */
-  B200FE_VARIANT_FFT = 1,        /* shared-memory radix-4 Stockham real FFT on the CUDA cores        */
+  B200FE_VARIANT_FFT = 1,        /* real FFT on the CUDA cores (register-resident warp FFT; Stockham fallback) */
   B200FE_VARIANT_DFT_GEMM = 2    /* folded DFT as a split-fp16 GEMM on tcgen05 tensor cores / TMEM   */
 } b200fe_variant;
 
@@ -110,7 +110,10 @@ int32_t b200fe_tables_pack(const b200fe_params* p, const float* window, const fl
  * the frame centre with window[0] == 0 (periodic Hann) and a triangular filterbank whose bins feed
  * at most two adjacent filters.  Returns B200FE_VARIANT_FFT / _DFT_GEMM, or an error when an
  * explicitly requested variant is not available.  Callers store the answer in params.variant;
- * forward calls given B200FE_VARIANT_AUTO use the FFT variant (they only see the device copy). */
+ * forward calls given B200FE_VARIANT_AUTO use the FFT variant (they only see the device copy).
+ * A forward call that says B200FE_VARIANT_DFT_GEMM with a blob this function would have refused
+ * cannot be detected on the host (no synchronisation): the kernel traps and the stream reports a
+ * CUDA error (B200FE_ERR_CUDA from the next call), it never returns garbage silently. */
 int32_t b200fe_tables_variant(const b200fe_params* p, const void* blob_host);
 
 /* ---- device entry points -------------------------------------------------------------------- */
@@ -174,6 +177,16 @@ int32_t b200fe_features_forward_host(const float* wave_host, int64_t R, int64_t 
                                      const void* tables, float* out_host, void* staging,
                                      size_t staging_bytes, int64_t chunk_rows, void* const* streams,
                                      int32_t n_streams);
+
+/* The same with 16-bit PCM rows on the host (what ASVspoof's FLAC files decode to before the reference's loader
+ * turns them into float32, maze5.py:297-351): the PCM crosses PCIe (half the bytes), a device kernel converts
+ * x / 32768 — exact in float32, so the features are bit-identical to the float32 call on the converted samples.
+ *   pcm_host  int16 [R][T];  staging >= b200fe_host_staging_bytes_i16(p, chunk_rows, T, n_streams)            */
+int64_t b200fe_host_staging_bytes_i16(const b200fe_params* p, int64_t chunk_rows, int64_t T, int32_t n_streams);
+int32_t b200fe_features_forward_host_i16(const int16_t* pcm_host, int64_t R, int64_t T, const b200fe_params* p,
+                                         const void* tables, float* out_host, void* staging,
+                                         size_t staging_bytes, int64_t chunk_rows, void* const* streams,
+                                         int32_t n_streams);
 
 /* Number of kernel launches the last b200fe_*_forward call on this thread enqueued (bench.py's
  * gpu_launches figure is counted from this). */
