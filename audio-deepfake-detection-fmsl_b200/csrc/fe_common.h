@@ -17,7 +17,7 @@ struct alignas(8) fe_c2 {
   float x, y;
 };
 
-#define FE_BLOB_MAGIC 0xB200FE01u
+#define FE_BLOB_MAGIC 0xB200FE02u
 
 // Header of the constant-table blob produced by b200fe_tables_pack (all offsets in bytes from the
 // start of the blob, 16-byte aligned).  The blob is position independent: the same bytes are valid
@@ -45,11 +45,10 @@ struct fe_blob_header {
   int32_t gemm_b_bytes;
   int32_t off_gemm_mid;    // float[2][gemm_kpairs]  true-unit weights of bin n_fft/4 (Re from a_e, Im from a_o)
   // sliding even/odd filter accumulators of the drain (fe_gemm_layout.h)
-  int32_t off_gemm_dw;     // fe_drain_w[gemm_nhalf + 1]   per GEMM column (+ bin n_fft/4): weights of the 4 accumulators
-  int32_t off_gemm_dctl;   // uint32[gemm_nhalf/8 + 1]     per 8-column batch: switch flags, bit 4*i + a
-  int32_t off_gemm_dids;   // fe_drain_ids[gemm_nhalf + 1] filter ids of the 4 accumulators after the column's switches
-  int32_t gemm_nbuf;       // emission buffers of the drain: 2 (indexed by column-group parity) or 4 (one per group)
-  int32_t reserved[6];
+  int32_t off_gemm_dw;     // fe_drain_w[gemm_nhalf/2 + 1]   per column pair (+ bin n_fft/4): weights of the 4 classes x 2 halves
+  int32_t off_gemm_dctl;   // uint32[gemm_nhalf/8 + 1]       per 4-pair batch: switch flags, bit 8*(pair % 4) + 2*a + h
+  int32_t off_gemm_dids;   // fe_drain_ids[gemm_nhalf/2 + 1] filter rows of the 8 halves after the pair's switches
+  int32_t reserved[7];
 };
 
 static inline int64_t fe_align16(int64_t v) { return (v + 15) & ~(int64_t)15; }

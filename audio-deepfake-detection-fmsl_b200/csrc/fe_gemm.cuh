@@ -98,94 +98,157 @@ FE_HD fe_tile_geo fe_tile_geometry(int tile, int tile_frames, int total_frames, 
 // three of them (the sample buffer holds 132 hop blocks)
 FE_HD int fe_tile_frames(int nF) { return 2 * nF < FE_GEMM_TILE_M ? 2 * nF : FE_GEMM_TILE_M; }
 
-// One production unit = 16 sample pairs j = j0 .. j0+15 of one frame.  The
-// scale is folded into the fold:  bs = b*s ; a_e*s = fma(f, s, bs) ; a_o*s = fma(f, s, -bs)  (s is a power of
-// two, so both are exactly (f +- b)*s) and bin n_fft/4 is accumulated from the SCALED values with the
-// interleaved weight table midc[j] = (j even ? Re weight : Im weight) (four 16-byte broadcast loads per unit).
-FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scale, const float* midc,
-                                  float& mid_re, float& mid_im, fe_u4* chunk) {
-  uint32_t hi[4][4], lo[4][4];
+// Packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2: one issue slot for two lanes); plain C++ on the host.
+struct fe_f2 {
+  float x, y;
+};
+FE_HD fe_f2 fe_add2(fe_f2 a, fe_f2 b) {
+#ifdef __CUDA_ARCH__
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return fe_f2{r.x, r.y};
+#else
+  return fe_f2{a.x + b.x, a.y + b.y};
+#endif
+}
+FE_HD fe_f2 fe_mul2(fe_f2 a, fe_f2 b) {
+#ifdef __CUDA_ARCH__
+  const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return fe_f2{r.x, r.y};
+#else
+  return fe_f2{a.x * b.x, a.y * b.y};
+#endif
+}
+FE_HD fe_f2 fe_fma2(fe_f2 a, fe_f2 b, fe_f2 c) {
+#ifdef __CUDA_ARCH__
+  const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  return fe_f2{r.x, r.y};
+#else
+  return fe_f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)};
+#endif
+}
+
+// Two floats -> packed fp16 pair (first in the low half, round to nearest) and the packed fp16 pair of the residuals
+// v - fp16(v) (exact in fp32): the hi / lo operands of the split-fp16 products.
+FE_HD void fe_split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 back = __half22float2(h);
+  const float2 r = __ffma2_rn(back, make_float2(-1.0f, -1.0f), make_float2(a, b));   // (a, b) - back, exact
+  const __half2 l = __floats2half2_rn(r.x, r.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+#else
+  float ra, rb;
+  hi = fe_pack_hi(a, b, ra, rb);
+  lo = fe_pack_lo(ra, rb);
+#endif
+}
+
+// One production unit = 16 sample pairs j = j0 .. j0+15 of one frame, for ONE pass:
+//   pass 0: a[i] = (x[c+j] + x[c-j]) * s      pass 1: a[i] = (x[c+j] - x[c-j]) * s      (s: the frame's power-of-two scale)
+// evaluated as  bs = b*s ; a = fma(f, s, +-bs)  (exactly (f +- b)*s).  Even j feed the pass's first sub-GEMM (K index
+// i/2 of the unit's 8-wide K chunk), odd j the second; chunk[] = {even hi, even lo, odd hi, odd lo}, 16 bytes each.
+// Bin n_fft/4 is accumulated from the SCALED values: its real part only has even-j terms (pass 0), its imaginary part
+// only odd-j terms (pass 1); midw[u] = weight of sample pair j0 + 2u + PASS (8 consecutive floats, 16-byte aligned).
+template <int PASS>
+FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scale, const float* midw, float& mid, fe_u4* chunk) {
+  float a[16];
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    const int i0 = 4 * w;
-    float ae[4], ao[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float bs = bwd[i0 + u] * scale;
-      ae[u] = fmaf(fwd[i0 + u], scale, bs);
-      ao[u] = fmaf(fwd[i0 + u], scale, -bs);
-    }
-    const float m0 = midc[i0], m1 = midc[i0 + 1], m2 = midc[i0 + 2], m3 = midc[i0 + 3];
-    mid_re = fmaf(ae[0], m0, mid_re);
-    mid_im = fmaf(ao[1], m1, mid_im);
-    mid_re = fmaf(ae[2], m2, mid_re);
-    mid_im = fmaf(ao[3], m3, mid_im);
-    float r0, r1;
-    hi[0][w] = fe_pack_hi(ae[0], ae[2], r0, r1); lo[0][w] = fe_pack_lo(r0, r1);
-    hi[1][w] = fe_pack_hi(ae[1], ae[3], r0, r1); lo[1][w] = fe_pack_lo(r0, r1);
-    hi[2][w] = fe_pack_hi(ao[0], ao[2], r0, r1); lo[2][w] = fe_pack_lo(r0, r1);
-    hi[3][w] = fe_pack_hi(ao[1], ao[3], r0, r1); lo[3][w] = fe_pack_lo(r0, r1);
+  for (int i = 0; i < 16; ++i) {
+    const float bs = bwd[i] * scale;
+    a[i] = PASS == 0 ? fmaf(fwd[i], scale, bs) : fmaf(fwd[i], scale, -bs);
   }
 #pragma unroll
-  for (int sub = 0; sub < 4; ++sub) {
+  for (int u = 0; u < 8; ++u) mid = fmaf(a[2 * u + PASS], midw[u], mid);
+  uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    fe_split_pair(a[4 * w + 0], a[4 * w + 2], hi[0][w], lo[0][w]);
+    fe_split_pair(a[4 * w + 1], a[4 * w + 3], hi[1][w], lo[1][w]);
+  }
+#pragma unroll
+  for (int sub = 0; sub < 2; ++sub) {
     chunk[sub * 2 + 0] = fe_u4{hi[sub][0], hi[sub][1], hi[sub][2], hi[sub][3]};
     chunk[sub * 2 + 1] = fe_u4{lo[sub][0], lo[sub][1], lo[sub][2], lo[sub][3]};
   }
 }
 
-// ---- drain: sliding even/odd filter accumulators (tables: fe_gemm_layout.h) ------------------------------
+// ---- drain: sliding even/odd filter accumulators over column pairs (tables: fe_gemm_layout.h) ---------------------
 struct fe_drain_state {
-  float acc[4];
-  int off[4];   // element offset of the accumulator's filter row in the emission scratch (dummy row: none)
+  fe_f2 acc[4];   // class a: .x even columns, .y odd columns
+  int off[8];     // half 2a + h: BYTE offset of its filter's row in the emission scratch (dummy row: none)
 };
 
-// adds one finished accumulator to the frame's filter sum (e_col = this frame's column of the [filter + 1][128] array;
-// accumulators without a filter point at the dummy last row, so there is nothing to test)
-FE_HD void fe_drain_emit(float* e_col, int off, float v, float us2) { e_col[off] = fmaf(v, us2, e_col[off]); }
+// the walk of a column group starts with the halves already aimed at the filters of the group's first pair
+FE_HD void fe_drain_init(fe_drain_state& st, const fe_drain_ids& first) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a) st.acc[a] = fe_f2{0.0f, 0.0f};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st.off[i] = first.off[i];
+}
 
-// the (rare, thread-uniform) switches of one column
-FE_HD void fe_drain_switch(unsigned flags, fe_drain_ids ids, fe_drain_state& st, float* e_col, float us2) {
+// adds one finished half accumulator to the frame's filter sum (e_col = this frame's column of the [filter + 1][128]
+// array; halves without a filter point at the dummy last row, so there is nothing to test)
+FE_HD void fe_drain_emit(float* e_col, int off, float v, float us2) {
+  float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(e_col) + off);
+  *p = fmaf(v, us2, *p);
+}
+
+// the (thread-uniform) switches of one pair: bit 2a + h; classes without a switch are skipped by a uniform branch
+FE_HD void fe_drain_switch(unsigned flags, const fe_drain_ids& ids, fe_drain_state& st, float* e_col, float us2) {
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    if (flags & (1u << a)) {
-      fe_drain_emit(e_col, st.off[a], st.acc[a], us2);
-      st.acc[a] = 0.0f;
-      st.off[a] = ids.off[a];
+    if (flags & (3u << (2 * a))) {
+      if (flags & (1u << (2 * a))) {
+        fe_drain_emit(e_col, st.off[2 * a], st.acc[a].x, us2);
+        st.acc[a].x = 0.0f;
+        st.off[2 * a] = ids.off[2 * a];
+      }
+      if (flags & (2u << (2 * a))) {
+        fe_drain_emit(e_col, st.off[2 * a + 1], st.acc[a].y, us2);
+        st.acc[a].y = 0.0f;
+        st.off[2 * a + 1] = ids.off[2 * a + 1];
+      }
     }
   }
 }
 
-// NB consecutive columns starting at a multiple of 8 (ctl = the batch's switch word, w / ids at the first column)
-template <int NB>
-FE_HD void fe_drain_cols(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, const float* ce, const float* co,
-                         const float* se, const float* so, fe_drain_state& st, float* e_col, float us2) {
+// NP consecutive column pairs starting at a multiple of 4 pairs (ctl = the batch's switch word, wt = the pairs' weights,
+// already in registers; ids at the first pair); u, v = the pass's two accumulators (ce, co or se, so) at those 2*NP
+// columns.  The pass's share of the powers: (u + v)^2 for bin k, (u - v)^2 for bin n_fft/2 - k.
+template <int NP>
+FE_HD void fe_drain_pairs(const fe_drain_w* wt, const fe_drain_ids* ids, unsigned ctl, const float* u, const float* v,
+                          fe_drain_state& st, float* e_col, float us2) {
 #pragma unroll
-  for (int i = 0; i < NB; ++i) {
-    const float re1 = ce[i] + co[i], im1 = se[i] + so[i], re2 = ce[i] - co[i], im2 = so[i] - se[i];
-    const float p1 = fmaf(re1, re1, im1 * im1);  // |X[k]|^2 (scaled units)
-    const float p2 = fmaf(re2, re2, im2 * im2);  // |X[n_fft/2 - k]|^2
-    const unsigned fl = (ctl >> (4 * i)) & 15u;
-    if (fl) fe_drain_switch(fl, ids[i], st, e_col, us2);
-    const fe_drain_w t = w[i];
-    st.acc[0] = fmaf(p1, t.w[0], st.acc[0]);
-    st.acc[1] = fmaf(p1, t.w[1], st.acc[1]);
-    st.acc[2] = fmaf(p2, t.w[2], st.acc[2]);
-    st.acc[3] = fmaf(p2, t.w[3], st.acc[3]);
+  for (int p = 0; p < NP; ++p) {
+    const fe_f2 uu = fe_f2{u[2 * p], u[2 * p + 1]}, vv = fe_f2{v[2 * p], v[2 * p + 1]};
+    const fe_f2 s = fe_add2(uu, vv), d = fe_fma2(vv, fe_f2{-1.0f, -1.0f}, uu);
+    const fe_f2 p1 = fe_mul2(s, s), p2 = fe_mul2(d, d);
+    const unsigned fl = (ctl >> (8 * p)) & 255u;
+    if (fl) fe_drain_switch(fl, ids[p], st, e_col, us2);
+    st.acc[0] = fe_fma2(p1, fe_f2{wt[p].w[0][0], wt[p].w[0][1]}, st.acc[0]);
+    st.acc[1] = fe_fma2(p1, fe_f2{wt[p].w[1][0], wt[p].w[1][1]}, st.acc[1]);
+    st.acc[2] = fe_fma2(p2, fe_f2{wt[p].w[2][0], wt[p].w[2][1]}, st.acc[2]);
+    st.acc[3] = fe_fma2(p2, fe_f2{wt[p].w[3][0], wt[p].w[3][1]}, st.acc[3]);
   }
 }
 
-// bin n_fft/4 (column index nhalf of the tables): only the lo-run accumulators
+// bin n_fft/4 (pair index nhalf/2 of the tables, even half only): only the ascending run's classes; p_mid = this
+// pass's share of the bin's power (Re^2 in pass 0, Im^2 in pass 1)
 FE_HD void fe_drain_mid(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, float p_mid, fe_drain_state& st,
                         float* e_col, float us2) {
-  const unsigned fl = ctl & 3u;
+  const unsigned fl = ctl & 0x05u;   // halves (class 0, even) and (class 1, even)
   if (fl) fe_drain_switch(fl, ids[0], st, e_col, us2);
-  st.acc[0] = fmaf(p_mid, w[0].w[0], st.acc[0]);
-  st.acc[1] = fmaf(p_mid, w[0].w[1], st.acc[1]);
+  st.acc[0].x = fmaf(p_mid, w[0].w[0][0], st.acc[0].x);
+  st.acc[1].x = fmaf(p_mid, w[0].w[1][0], st.acc[1].x);
 }
 
 FE_HD void fe_drain_flush(fe_drain_state& st, float* e_col, float us2) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) fe_drain_emit(e_col, st.off[a], st.acc[a], us2);
+  for (int a = 0; a < 4; ++a) {
+    fe_drain_emit(e_col, st.off[2 * a], st.acc[a].x, us2);
+    fe_drain_emit(e_col, st.off[2 * a + 1], st.acc[a].y, us2);
+  }
 }
 
 #endif  // FE_GEMM_CUH_

@@ -26,7 +26,7 @@ gemm_geom geometry(const b200fe_params* p) {
   const int kpairs = p->win_length / 2;
   const int nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return g;
-  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM
+  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return g;  // 2 passes x 2 accumulators of nhalf columns fit TMEM
   g.ok = true;
   g.kpairs = kpairs;
   g.nhalf = nhalf;
@@ -49,27 +49,27 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
   h->off_gemm_mid = (int32_t)off;
   off = fe_align16(off + (int64_t)2 * g.kpairs * 4);
   h->off_gemm_dw = (int32_t)off;
-  off = fe_align16(off + (int64_t)(g.nhalf + 1) * sizeof(fe_drain_w));
+  off = fe_align16(off + (int64_t)(g.nhalf / 2 + 1) * sizeof(fe_drain_w));
   h->off_gemm_dctl = (int32_t)off;
   off = fe_align16(off + (int64_t)(g.nhalf / 8 + 1) * 4);
   h->off_gemm_dids = (int32_t)off;
-  off = fe_align16(off + (int64_t)(g.nhalf + 1) * sizeof(fe_drain_ids));
+  off = fe_align16(off + (int64_t)(g.nhalf / 2 + 1) * sizeof(fe_drain_ids));
   h->gemm_ok = 1;  // provisional: fe_gemm_pack clears it when the window / filterbank do not qualify
   return off;
 }
 
-// Drain tables (fe_gemm_layout.h): per column the weights of the four sliding
-// accumulators, the switch flags and the filter ids after the switches.  Returns false when the filterbank
-// does not qualify (a bin with two filters of the same parity, or a filter shared by non-adjacent groups).
+// Drain tables (fe_gemm_layout.h): per column pair the weights of the four accumulator classes x two halves, the
+// switch flags and the filter rows after the switches.  Returns false when the filterbank does not qualify (a bin
+// with two filters of the same parity).
 static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, int nhalf, char* base) {
   if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nfil > FE_GEMM_MAX_FILTERS) return false;
   fe_drain_w* dw = (fe_drain_w*)(base + h->off_gemm_dw);
   uint32_t* dctl = (uint32_t*)(base + h->off_gemm_dctl);
   fe_drain_ids* dids = (fe_drain_ids*)(base + h->off_gemm_dids);
-  memset(dw, 0, (size_t)(nhalf + 1) * sizeof(fe_drain_w));
+  const int npairs = nhalf / 2;
+  memset(dw, 0, (size_t)(npairs + 1) * sizeof(fe_drain_w));
   memset(dctl, 0, (size_t)(nhalf / 8 + 1) * 4);
-  const int nyq = 2 * nhalf, cpg = nhalf / FE_DRAIN_GROUPS;
-  std::vector<unsigned> touched(nfil, 0u);
+  const int nyq = 2 * nhalf, ppg = npairs / FE_DRAIN_GROUPS;   // pairs per column group
   // filter of parity `par` with weight on `bin` (-1: none, -2: more than one)
   auto filter_of = [&](int bin, int par) {
     int f_found = -1;
@@ -78,39 +78,37 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
     return f_found;
   };
   for (int g = 0; g < FE_DRAIN_GROUPS; ++g) {
-    int cur[4] = {-1, -1, -1, -1};
-    const int k_end = (g + 1) * cpg + (g == FE_DRAIN_GROUPS - 1 ? 1 : 0);  // the last group also takes bin n_fft/4
-    for (int k = g * cpg; k < k_end; ++k) {
+    int cur[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
+    // the last group also takes bin n_fft/4 as the even column of one more (half) pair
+    const int p_end = (g + 1) * ppg + (g == FE_DRAIN_GROUPS - 1 ? 1 : 0);
+    for (int p = g * ppg; p < p_end; ++p) {
       unsigned flags = 0;
-      for (int run = 0; run < 2; ++run) {
-        if (k == nhalf && run == 1) continue;
-        const int bin = run == 0 ? k : nyq - k;
-        for (int par = 0; par < 2; ++par) {
-          const int a = 2 * run + par;
-          const int f = filter_of(bin, par);
-          if (f == -2) return false;
-          if (f < 0) continue;
-          dw[k].w[a] = fbank[(int64_t)bin * nfil + f];
-          touched[f] |= 1u << g;
-          if (f != cur[a]) { flags |= 1u << a; cur[a] = f; }
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k = 2 * p + hh;
+        if (k > nhalf) continue;                     // the odd half of the bin-n_fft/4 entry does not exist
+        for (int run = 0; run < 2; ++run) {
+          if (k == nhalf && run == 1) continue;      // bin n_fft/4 belongs to the ascending run only
+          const int bin = run == 0 ? k : nyq - k;
+          for (int par = 0; par < 2; ++par) {
+            const int a = 2 * run + par;
+            const int f = filter_of(bin, par);
+            if (f == -2) return false;
+            if (f < 0) continue;
+            dw[p].w[a][hh] = fbank[(int64_t)bin * nfil + f];
+            if (f != cur[a][hh]) {
+              if (p != g * ppg) flags |= 1u << (2 * a + hh);   // the group's first pair: the walk starts aimed at it
+              cur[a][hh] = f;
+            }
+          }
         }
       }
-      for (int a = 0; a < 4; ++a) dids[k].off[a] = (int16_t)((cur[a] < 0 ? nfil : cur[a]) * FE_GEMM_TILE_M);
-      dctl[k / 8] |= flags << (4 * (k % 8));
+      for (int a = 0; a < 4; ++a)
+        for (int hh = 0; hh < 2; ++hh)
+          dids[p].off[2 * a + hh] = (int16_t)((cur[a][hh] < 0 ? nfil : cur[a][hh]) * FE_GEMM_TILE_M * 4);
+      dctl[p / 4] |= flags << (8 * (p % 4));
     }
   }
-  // Column groups that share a filter must emit into different buffers.  Two buffers indexed by group parity do
-  // when a filter is only ever shared by adjacent groups; otherwise every group gets its own buffer (if the
-  // n_filter x 128 arrays still fit the 64 KB of A slots they alias).
-  bool adjacent_only = true;
-  for (int f = 0; f < nfil; ++f) {
-    const unsigned m = touched[f];
-    if (m == 0) continue;
-    const unsigned low = m & (0u - m);
-    if (m != low && m != (low | (low << 1))) adjacent_only = false;
-  }
-  h->gemm_nbuf = adjacent_only ? 2 : FE_DRAIN_GROUPS;
-  return h->gemm_nbuf * (nfil + 1) * FE_GEMM_TILE_M * 4 <= 2 * 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M);   // both A slots (+1: the dummy row)
+  return true;
 }
 
 int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* window, const float* fbank,
