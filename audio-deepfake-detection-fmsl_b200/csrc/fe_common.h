@@ -48,7 +48,8 @@ struct fe_blob_header {
   int32_t off_gemm_dw;     // fe_drain_w[gemm_nhalf/2 + 1]   per column pair (+ bin n_fft/4): weights of the 4 classes x 2 halves
   int32_t off_gemm_dctl;   // uint32[gemm_nhalf/8 + 1]       per 4-pair batch: switch flags, bit 8*(pair % 4) + 2*a + h
   int32_t off_gemm_dids;   // fe_drain_ids[gemm_nhalf/2 + 1] filter rows of the 8 halves after the pair's switches
-  int32_t reserved[7];
+  int32_t gemm_nbuf;       // emission buffers of the drain: 2 (indexed by column-group parity) or 4 (one per group)
+  int32_t reserved[6];
 };
 
 static inline int64_t fe_align16(int64_t v) { return (v + 15) & ~(int64_t)15; }

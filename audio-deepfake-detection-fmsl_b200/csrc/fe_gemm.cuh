@@ -58,46 +58,6 @@ FE_HD uint32_t fe_pack_lo(float a, float b) {
   return fe_pack_hi(a, b, ra, rb);
 }
 
-// Per-frame power-of-two scale: `bound` >= max |a_e|, |a_o| of the frame (2 * max|x| over its two hop
-// blocks).  scale * bound lies in [2^13, 2^14), so the fp16 hi parts keep 11 significant bits and the lo
-// parts stay normal numbers; `unscale` = 1 / (scale * 2^14) undoes it (and the 2^14 of the DFT tiles)
-// on the amplitude, i.e. power_true = power_acc * unscale^2.
-FE_HD void fe_gemm_frame_scale(float bound, float& scale, float& unscale) {
-  const uint32_t eb = (fe_f2u(bound) >> 23) & 0xffu;
-  int e = (int)eb - 127;               // bound in [2^e, 2^(e+1))
-  if (eb == 0u || eb == 0xffu) e = FE_GEMM_A_SCALE_LOG2;   // zero / subnormal / non-finite: scale 1
-  int s = FE_GEMM_A_SCALE_LOG2 - e;
-  s = s > 100 ? 100 : (s < -100 ? -100 : s);
-  scale = fe_u2f((uint32_t)(s + 127) << 23);
-  unscale = fe_u2f((uint32_t)(-s - FE_GEMM_B_SCALE_LOG2 + 127) << 23);
-}
-
-// =====================================================================================================
-// Streaming kernel (fe_stream.cu)
-// =====================================================================================================
-
-// Tile geometry of the frame stream.  The launch's rows are one stream of frames g = row * nF + t; a tile takes
-// `tile_frames` consecutive stream frames.  Hop block v of a row (samples [(v-1) hop, v hop); v = 0 and v = nF are
-// the reflect-padded edges) has stream index row (nF+1) + v; frame (row, t) reads blocks t (backward half) and
-// t + 1 (forward half), so a tile needs the nv consecutive stream blocks sv0 .. sv0 + nv - 1.
-struct fe_tile_geo {
-  int g0, count, row0, row_last, sv0, nv;
-};
-FE_HD fe_tile_geo fe_tile_geometry(int tile, int tile_frames, int total_frames, int nF) {
-  fe_tile_geo t;
-  t.g0 = tile * tile_frames;
-  t.count = total_frames - t.g0 < tile_frames ? total_frames - t.g0 : tile_frames;
-  t.row0 = t.g0 / nF;
-  const int g_last = t.g0 + t.count - 1;
-  t.row_last = g_last / nF;
-  t.sv0 = t.g0 + t.row0;
-  t.nv = t.count + (t.row_last - t.row0) + 1;
-  return t;
-}
-// frames per tile: 128 (the TMEM lanes) unless the utterances are so short that 128 frames would span more than
-// three of them (the sample buffer holds 132 hop blocks)
-FE_HD int fe_tile_frames(int nF) { return 2 * nF < FE_GEMM_TILE_M ? 2 * nF : FE_GEMM_TILE_M; }
-
 // Packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2: one issue slot for two lanes); plain C++ on the host.
 struct fe_f2 {
   float x, y;
@@ -144,30 +104,75 @@ FE_HD void fe_split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
 #endif
 }
 
-// One production unit = 16 sample pairs j = j0 .. j0+15 of one frame, for ONE pass:
-//   pass 0: a[i] = (x[c+j] + x[c-j]) * s      pass 1: a[i] = (x[c+j] - x[c-j]) * s      (s: the frame's power-of-two scale)
-// evaluated as  bs = b*s ; a = fma(f, s, +-bs)  (exactly (f +- b)*s).  Even j feed the pass's first sub-GEMM (K index
-// i/2 of the unit's 8-wide K chunk), odd j the second; chunk[] = {even hi, even lo, odd hi, odd lo}, 16 bytes each.
-// Bin n_fft/4 is accumulated from the SCALED values: its real part only has even-j terms (pass 0), its imaginary part
-// only odd-j terms (pass 1); midw[u] = weight of sample pair j0 + 2u + PASS (8 consecutive floats, 16-byte aligned).
-template <int PASS>
-FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scale, const float* midw, float& mid, fe_u4* chunk) {
-  float a[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float bs = bwd[i] * scale;
-    a[i] = PASS == 0 ? fmaf(fwd[i], scale, bs) : fmaf(fwd[i], scale, -bs);
-  }
-#pragma unroll
-  for (int u = 0; u < 8; ++u) mid = fmaf(a[2 * u + PASS], midw[u], mid);
-  uint32_t hi[2][4], lo[2][4];
+// Per-frame power-of-two scale: `bound` >= max |a_e|, |a_o| of the frame (2 * max|x| over its two hop
+// blocks).  scale * bound lies in [2^13, 2^14), so the fp16 hi parts keep 11 significant bits and the lo
+// parts stay normal numbers; `unscale` = 1 / (scale * 2^14) undoes it (and the 2^14 of the DFT tiles)
+// on the amplitude, i.e. power_true = power_acc * unscale^2.
+FE_HD void fe_gemm_frame_scale(float bound, float& scale, float& unscale) {
+  const uint32_t eb = (fe_f2u(bound) >> 23) & 0xffu;
+  int e = (int)eb - 127;               // bound in [2^e, 2^(e+1))
+  if (eb == 0u || eb == 0xffu) e = FE_GEMM_A_SCALE_LOG2;   // zero / subnormal / non-finite: scale 1
+  int s = FE_GEMM_A_SCALE_LOG2 - e;
+  s = s > 100 ? 100 : (s < -100 ? -100 : s);
+  scale = fe_u2f((uint32_t)(s + 127) << 23);
+  unscale = fe_u2f((uint32_t)(-s - FE_GEMM_B_SCALE_LOG2 + 127) << 23);
+}
+
+// =====================================================================================================
+// Streaming kernel (fe_stream.cu)
+// =====================================================================================================
+
+// Tile geometry of the frame stream.  The launch's rows are one stream of frames g = row * nF + t; a tile takes
+// `tile_frames` consecutive stream frames.  Hop block v of a row (samples [(v-1) hop, v hop); v = 0 and v = nF are
+// the reflect-padded edges) has stream index row (nF+1) + v; frame (row, t) reads blocks t (backward half) and
+// t + 1 (forward half), so a tile needs the nv consecutive stream blocks sv0 .. sv0 + nv - 1.
+struct fe_tile_geo {
+  int g0, count, row0, row_last, sv0, nv;
+};
+FE_HD fe_tile_geo fe_tile_geometry(int tile, int tile_frames, int total_frames, int nF) {
+  fe_tile_geo t;
+  t.g0 = tile * tile_frames;
+  t.count = total_frames - t.g0 < tile_frames ? total_frames - t.g0 : tile_frames;
+  t.row0 = t.g0 / nF;
+  const int g_last = t.g0 + t.count - 1;
+  t.row_last = g_last / nF;
+  t.sv0 = t.g0 + t.row0;
+  t.nv = t.count + (t.row_last - t.row0) + 1;
+  return t;
+}
+// frames per tile: 128 (the TMEM lanes) unless the utterances are so short that 128 frames would span more than
+// three of them (the sample buffer holds 132 hop blocks)
+FE_HD int fe_tile_frames(int nF) { return 2 * nF < FE_GEMM_TILE_M ? 2 * nF : FE_GEMM_TILE_M; }
+
+// One production unit = 16 sample pairs j = j0 .. j0+15 of one frame.  The
+// scale is folded into the fold:  bs = b*s ; a_e*s = fma(f, s, bs) ; a_o*s = fma(f, s, -bs)  (s is a power of
+// two, so both are exactly (f +- b)*s) and bin n_fft/4 is accumulated from the SCALED values with the
+// interleaved weight table midc[j] = (j even ? Re weight : Im weight) (four 16-byte broadcast loads per unit).
+FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scale, const float* midc,
+                                  float& mid_re, float& mid_im, fe_u4* chunk) {
+  uint32_t hi[4][4], lo[4][4];
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    fe_split_pair(a[4 * w + 0], a[4 * w + 2], hi[0][w], lo[0][w]);
-    fe_split_pair(a[4 * w + 1], a[4 * w + 3], hi[1][w], lo[1][w]);
+    const int i0 = 4 * w;
+    float ae[4], ao[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float bs = bwd[i0 + u] * scale;
+      ae[u] = fmaf(fwd[i0 + u], scale, bs);
+      ao[u] = fmaf(fwd[i0 + u], scale, -bs);
+    }
+    const float m0 = midc[i0], m1 = midc[i0 + 1], m2 = midc[i0 + 2], m3 = midc[i0 + 3];
+    mid_re = fmaf(ae[0], m0, mid_re);
+    mid_im = fmaf(ao[1], m1, mid_im);
+    mid_re = fmaf(ae[2], m2, mid_re);
+    mid_im = fmaf(ao[3], m3, mid_im);
+    fe_split_pair(ae[0], ae[2], hi[0][w], lo[0][w]);
+    fe_split_pair(ae[1], ae[3], hi[1][w], lo[1][w]);
+    fe_split_pair(ao[0], ao[2], hi[2][w], lo[2][w]);
+    fe_split_pair(ao[1], ao[3], hi[3][w], lo[3][w]);
   }
 #pragma unroll
-  for (int sub = 0; sub < 2; ++sub) {
+  for (int sub = 0; sub < 4; ++sub) {
     chunk[sub * 2 + 0] = fe_u4{hi[sub][0], hi[sub][1], hi[sub][2], hi[sub][3]};
     chunk[sub * 2 + 1] = fe_u4{lo[sub][0], lo[sub][1], lo[sub][2], lo[sub][3]};
   }
@@ -213,28 +218,30 @@ FE_HD void fe_drain_switch(unsigned flags, const fe_drain_ids& ids, fe_drain_sta
   }
 }
 
-// NP consecutive column pairs starting at a multiple of 4 pairs (ctl = the batch's switch word, wt = the pairs' weights,
-// already in registers; ids at the first pair); u, v = the pass's two accumulators (ce, co or se, so) at those 2*NP
-// columns.  The pass's share of the powers: (u + v)^2 for bin k, (u - v)^2 for bin n_fft/2 - k.
+// NP consecutive column pairs starting at a multiple of 4 pairs (ctl = the batch's switch word, w / ids at the first
+// pair): |X[k]|^2 = (ce+co)^2 + (se+so)^2 and |X[n_fft/2 - k]|^2 = (ce-co)^2 + (so-se)^2 for two columns at a time.
 template <int NP>
-FE_HD void fe_drain_pairs(const fe_drain_w* wt, const fe_drain_ids* ids, unsigned ctl, const float* u, const float* v,
-                          fe_drain_state& st, float* e_col, float us2) {
+FE_HD void fe_drain_pairs(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, const float* ce, const float* co,
+                          const float* se, const float* so, fe_drain_state& st, float* e_col, float us2) {
+  const fe_f2 neg = fe_f2{-1.0f, -1.0f};
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
-    const fe_f2 uu = fe_f2{u[2 * p], u[2 * p + 1]}, vv = fe_f2{v[2 * p], v[2 * p + 1]};
-    const fe_f2 s = fe_add2(uu, vv), d = fe_fma2(vv, fe_f2{-1.0f, -1.0f}, uu);
-    const fe_f2 p1 = fe_mul2(s, s), p2 = fe_mul2(d, d);
+    const fe_f2 c0 = fe_f2{ce[2 * p], ce[2 * p + 1]}, c1 = fe_f2{co[2 * p], co[2 * p + 1]};
+    const fe_f2 s0 = fe_f2{se[2 * p], se[2 * p + 1]}, s1 = fe_f2{so[2 * p], so[2 * p + 1]};
+    const fe_f2 re1 = fe_add2(c0, c1), im1 = fe_add2(s0, s1), re2 = fe_fma2(c1, neg, c0), im2 = fe_fma2(s0, neg, s1);
+    const fe_f2 p1 = fe_fma2(re1, re1, fe_mul2(im1, im1));   // |X[k]|^2 (scaled units)
+    const fe_f2 p2 = fe_fma2(re2, re2, fe_mul2(im2, im2));   // |X[n_fft/2 - k]|^2
     const unsigned fl = (ctl >> (8 * p)) & 255u;
     if (fl) fe_drain_switch(fl, ids[p], st, e_col, us2);
-    st.acc[0] = fe_fma2(p1, fe_f2{wt[p].w[0][0], wt[p].w[0][1]}, st.acc[0]);
-    st.acc[1] = fe_fma2(p1, fe_f2{wt[p].w[1][0], wt[p].w[1][1]}, st.acc[1]);
-    st.acc[2] = fe_fma2(p2, fe_f2{wt[p].w[2][0], wt[p].w[2][1]}, st.acc[2]);
-    st.acc[3] = fe_fma2(p2, fe_f2{wt[p].w[3][0], wt[p].w[3][1]}, st.acc[3]);
+    const fe_drain_w t = w[p];
+    st.acc[0] = fe_fma2(p1, fe_f2{t.w[0][0], t.w[0][1]}, st.acc[0]);
+    st.acc[1] = fe_fma2(p1, fe_f2{t.w[1][0], t.w[1][1]}, st.acc[1]);
+    st.acc[2] = fe_fma2(p2, fe_f2{t.w[2][0], t.w[2][1]}, st.acc[2]);
+    st.acc[3] = fe_fma2(p2, fe_f2{t.w[3][0], t.w[3][1]}, st.acc[3]);
   }
 }
 
-// bin n_fft/4 (pair index nhalf/2 of the tables, even half only): only the ascending run's classes; p_mid = this
-// pass's share of the bin's power (Re^2 in pass 0, Im^2 in pass 1)
+// bin n_fft/4 (pair index nhalf/2 of the tables, even half only): only the ascending run's classes
 FE_HD void fe_drain_mid(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, float p_mid, fe_drain_state& st,
                         float* e_col, float us2) {
   const unsigned fl = ctl & 0x05u;   // halves (class 0, even) and (class 1, even)

@@ -22,23 +22,15 @@
 #define FE_GEMM_A_SCALE_LOG2 13   // per frame: 2*max|x| is scaled into [2^13, 2^14)
 #define FE_GEMM_STAGE_J 32        // sample pairs per pipeline stage: one K=16 MMA step per sub-GEMM
 
-// ---- passes ------------------------------------------------------------------------------------------------
-// The four sums are computed in two PASSES per tile, each with its own half of TMEM (2 x n_fft/4 columns):
-//   pass 0 (cos pair):  ce, co from the a_e tiles  ->  Re X[k] = ce + co,  Re X[n_fft/2 - k] = ce - co
-//   pass 1 (sin pair):  se, so from the a_o tiles  ->  Im X[k] = se + so,  Im X[n_fft/2 - k] = so - se
-// The filterbank is linear in the power |X|^2 = Re^2 + Im^2, so each pass adds its own share
-// sum_k w[k] (u[k] +- v[k])^2 to the frame's filter sums.  While the drain warps reduce one pass's accumulators the
-// tensor pipe already fills the other half of TMEM with the next pass: nothing waits for TMEM.
-//
 // ---- drain tables ----------------------------------------------------------------------------------------
-// A drain thread owns one frame (TMEM lane) and one of FE_DRAIN_GROUPS column groups (nhalf / 2 consecutive GEMM
+// A drain thread owns one frame (TMEM lane) and one of FE_DRAIN_GROUPS column groups (nhalf / 4 consecutive GEMM
 // columns).  Column k carries bin k (the ascending "lo" run) and bin n_fft/2 - k (the descending "hi" run).  Every
 // bin may have at most one even-indexed and one odd-indexed filter with non-zero weight (true for triangular
 // banks), so each run needs two accumulators: class a = 2*run + parity.  Columns are processed in PAIRS (2p, 2p+1)
-// with packed fp32x2 arithmetic, so every class has two independent halves h (even / odd column), each with its own
-// target filter: half (a, h) is emitted (added to the frame's filter sum) and re-targeted before pair p whenever the
-// filter of class a at column 2p + h differs from the one at column 2p + h - 2 ("switch").  Switches are the same
-// for all threads: table driven and branch-uniform.
+// with packed fp32x2 arithmetic (one issue slot for two columns), so every class has two independent halves h (even /
+// odd column), each with its own target filter: half (a, h) is emitted (added to the frame's filter sum) and
+// re-targeted before pair p whenever the filter of class a at column 2p + h differs from the one at column 2p + h - 2
+// ("switch").  Switches are the same for all threads: table driven and branch-uniform.
 struct alignas(16) fe_drain_w {
   float w[4][2];     // per class a: weights at columns (2p, 2p+1); classes 0,1: bin k (even, odd filter); 2,3: bin n_fft/2 - k
 };
@@ -47,19 +39,16 @@ struct alignas(16) fe_drain_ids {
                      // row in the frame-major emission scratch; n_filter * 512 (a dummy row) while it has none.  The first
                      // pair of a column group carries no switch flags: the walk starts from that pair's entry.
 };
-#define FE_DRAIN_GROUPS 2   // column groups (drain warps per TMEM lane quarter)
+#define FE_DRAIN_GROUPS 4   // column groups (warps per TMEM lane quarter)
 
 // UMMA K-major, no-swizzle operand tile of `rows` rows x 16 K-values (one K=16 MMA step):
 // [K chunk of 8][row][8 halfs] -> descriptor LBO (K-chunk stride) = rows*16 B, SBO (8-row group) = 128 B.
 FE_HD int fe_gemm_operand_offset(int rows, int r, int kk) { return (kk >> 3) * rows * 16 + r * 16 + (kk & 7) * 2; }
 FE_HD int fe_gemm_tile_bytes(int rows) { return 2 * rows * 16; }
-// DFT operand tiles in the blob: per stage (32 sample pairs) [sub-GEMM 4: ce co se so][flavour 2: hi lo]; a pass
-// takes the stage's pair of sub-GEMMs: [sub 2][flavour 2] = one "pair-stage" (the second half of the stage for pass 1)
+// a stage holds [sub-GEMM 4: ce co se so][flavour 2: hi lo] tiles
 FE_HD int fe_gemm_b_tile_offset(int nhalf, int sub, int flav) { return (sub * 2 + flav) * fe_gemm_tile_bytes(nhalf); }
 FE_HD int fe_gemm_b_stage_bytes(int nhalf) { return 8 * fe_gemm_tile_bytes(nhalf); }
-FE_HD int fe_gemm_b_pair_bytes(int nhalf) { return 4 * fe_gemm_tile_bytes(nhalf); }
-// A tiles of one pair-stage: [sub of the pair 2: even j, odd j][flavour 2: hi lo]
 FE_HD int fe_gemm_a_tile_offset(int sub, int flav) { return (sub * 2 + flav) * fe_gemm_tile_bytes(FE_GEMM_TILE_M); }
-FE_HD int fe_gemm_a_pair_bytes() { return 4 * fe_gemm_tile_bytes(FE_GEMM_TILE_M); }
+FE_HD int fe_gemm_a_stage_bytes() { return 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M); }
 
 #endif  // FE_GEMM_LAYOUT_H_

@@ -26,7 +26,7 @@ gemm_geom geometry(const b200fe_params* p) {
   const int kpairs = p->win_length / 2;
   const int nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return g;
-  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return g;  // 2 passes x 2 accumulators of nhalf columns fit TMEM
+  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM
   g.ok = true;
   g.kpairs = kpairs;
   g.nhalf = nhalf;
@@ -60,7 +60,7 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
 
 // Drain tables (fe_gemm_layout.h): per column pair the weights of the four accumulator classes x two halves, the
 // switch flags and the filter rows after the switches.  Returns false when the filterbank does not qualify (a bin
-// with two filters of the same parity).
+// with two filters of the same parity, or emission buffers that do not fit the A slots they alias).
 static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, int nhalf, char* base) {
   if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nfil > FE_GEMM_MAX_FILTERS) return false;
   fe_drain_w* dw = (fe_drain_w*)(base + h->off_gemm_dw);
@@ -70,6 +70,7 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
   memset(dw, 0, (size_t)(npairs + 1) * sizeof(fe_drain_w));
   memset(dctl, 0, (size_t)(nhalf / 8 + 1) * 4);
   const int nyq = 2 * nhalf, ppg = npairs / FE_DRAIN_GROUPS;   // pairs per column group
+  std::vector<unsigned> touched(nfil, 0u);
   // filter of parity `par` with weight on `bin` (-1: none, -2: more than one)
   auto filter_of = [&](int bin, int par) {
     int f_found = -1;
@@ -95,6 +96,7 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
             if (f == -2) return false;
             if (f < 0) continue;
             dw[p].w[a][hh] = fbank[(int64_t)bin * nfil + f];
+            touched[f] |= 1u << g;
             if (f != cur[a][hh]) {
               if (p != g * ppg) flags |= 1u << (2 * a + hh);   // the group's first pair: the walk starts aimed at it
               cur[a][hh] = f;
@@ -108,7 +110,18 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
       dctl[p / 4] |= flags << (8 * (p % 4));
     }
   }
-  return true;
+  // Column groups that share a filter must emit into different buffers.  Two buffers indexed by group parity do
+  // when a filter is only ever shared by adjacent groups; otherwise every group gets its own buffer (if the
+  // n_filter x 128 arrays still fit the 64 KB of A slots they alias).
+  bool adjacent_only = true;
+  for (int f = 0; f < nfil; ++f) {
+    const unsigned m = touched[f];
+    if (m == 0) continue;
+    const unsigned low = m & (0u - m);
+    if (m != low && m != (low | (low << 1))) adjacent_only = false;
+  }
+  h->gemm_nbuf = adjacent_only ? 2 : FE_DRAIN_GROUPS;
+  return h->gemm_nbuf * (nfil + 1) * FE_GEMM_TILE_M * 4 <= 2 * 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M);   // both A slots (+1: the dummy row)
 }
 
 int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* window, const float* fbank,

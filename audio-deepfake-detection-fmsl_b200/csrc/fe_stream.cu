@@ -4,24 +4,25 @@
 // frames = the 128 TMEM lanes of one M=128 MMA, whatever utterances they belong to, so every tile is full.
 // One persistent CTA per SM walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...
 //
-// A tile is computed in two PASSES (fe_gemm_layout.h): pass 0 = the cos pair (ce, co) from the a_e tiles, pass 1 = the
-// sin pair (se, so) from the a_o tiles.  Each pass owns one half of TMEM (2 x n_fft/4 columns), and the filterbank is
-// linear in Re^2 + Im^2, so a pass is drained on its own: while the drain warps reduce pass g the tensor pipe fills the
-// other half with pass g+1 and the producers already stage pass g+2.  Nothing in the steady state waits for TMEM.
-//
-// Warp roles (20 warps, 96 registers per thread):
-//    0- 7  drain      warp = (TMEM lane quarter, column group): tcgen05.ld of the pass's two accumulators, packed
-//                     fp32x2 powers and sliding even/odd triangular-filter sums over column pairs; after pass 1:
-//                     finalize = the tile's energies -> workspace [row][filter][frame] (+ per-group maximum for top_db)
-//    8-15  producers  at the start of a tile: max|x| per hop block -> per-frame power-of-two scale; then thread = (frame,
-//                     K half): fold + scale + fp16 hi/lo split of 16 sample pairs into the UMMA A tiles of one pair-stage
-//                     (ring of nA slots of 16 KB)
-//   16-17  MMA        one issuing thread per sub-GEMM of the pair: 3 tcgen05.mma (M=128, N=n_fft/4, K=16: hi*hi + lo*hi
-//                     + hi*lo) per pair-stage, tcgen05.commit -> mbarriers
-//   18     samples    per tile: the hop blocks the tile's frames need, once each, as a handful of TMA tensor boxes
-//                     {32 floats, hop/32, 2^k hop blocks} with the 128-byte swizzle (hop blocks sit densely in shared
-//                     memory, lane <-> frame reads stay conflict-free); reflect-padded edge blocks with plain loads
-//   19     operands   per pair-stage the 16 KB of DFT operand tiles (ring of nB slots), one bulk copy each
+//   loader warp   per tile: the hop blocks the tile's frames need, once each, as a handful of TMA tensor boxes
+//                 {32 floats, hop/32, 2^k hop blocks} with the 128-byte swizzle: hop blocks sit densely in shared
+//                 memory and lane <-> frame reads are still conflict-free (consecutive blocks land on different
+//                 swizzle phases because hop/32 is odd or the phase advances by hop/32 mod 8).  A small 1-D bulk
+//                 copy costs the TMA unit ~90 cycles whatever its size (130 per tile took 12 k cycles), hence
+//                 boxes.  Reflect-padded edge blocks are synthesised with plain loads.  Per stage: the 32 KB of
+//                 DFT operand tiles.
+//   MMA warp      one thread: 12 tcgen05.mma (M=128, N=n_fft/4, K=16; 4 sub-GEMMs x 3 split-fp16 products) per
+//                 stage into the 4 TMEM accumulators, tcgen05.commit -> mbarriers
+//   16 worker warps, all doing the same thing in phases:
+//     scout       max|x| per hop block (shared memory) -> per-frame power-of-two scale
+//     produce     fold + scale + fp16 hi/lo split of 16 sample pairs per thread into the UMMA A tiles; the two
+//                 halves of the warps (0-7 / 8-15) take alternate stages, i.e. alternate A slots
+//     drain       tcgen05.ld of the four accumulators, powers, sliding even/odd triangular-filter sums
+//                 (fe_gemm_layout.h), all 16 warps: warp = (TMEM lane quarter, column group)
+//     finalize    energies of the tile -> workspace [row][filter][frame] (+ per-group maximum for top_db)
+// TMEM holds exactly the four accumulators (4 x 128 columns), so the MMAs of a tile and its drain cannot
+// overlap; everything else does: production runs one stage ahead of the MMAs, the next tile's samples and
+// operand stages are loaded during MMA tail and drain.
 #include <atomic>
 
 #include "fe_tc.cuh"
@@ -32,16 +33,15 @@
 
 namespace {
 
-constexpr int kDrainWarps = 8;
-constexpr int kDrainThreads = kDrainWarps * 32;
-constexpr int kProdWarp0 = 8, kProdWarps = 8;
-constexpr int kMmaWarp0 = 16, kNumMmaWarps = 2;
-constexpr int kSampLoaderWarp = 18, kOperandLoaderWarp = 19;
-constexpr int kThreads = 20 * 32;
+constexpr int kWorkerWarps = 16;
+constexpr int kWorkerThreads = kWorkerWarps * 32;
+constexpr int kMmaWarp0 = 16;   // warps 16, 17: MMA issuers, two sub-GEMMs each (ce, co / se, so)
+constexpr int kNumMmaWarps = 2;
+constexpr int kLoaderWarp = 18;
+constexpr int kThreads = 19 * 32;  // (registers are allocated per 4 warps: 20 warps' worth -> 96 registers per thread)
 constexpr int kTileM = FE_GEMM_TILE_M;
 constexpr int kMaxSlots = 132;                    // hop blocks of a tile: 128 + 1 + one more per utterance boundary
-constexpr int kAPairBytes = 4 * 2 * kTileM * 16;  // 16 KB: [sub 2][hi, lo] tiles of 128 rows x 16 K
-constexpr int kMaxRing = 4;                       // ring depths are chosen at launch from what fits shared memory
+constexpr int kAStageBytes = 8 * 2 * kTileM * 16; // 32 KB: [sub 4][hi, lo] tiles of 128 rows x 16 K
 
 struct stream_args {
   const float* wave;        // first row of the launch
@@ -53,47 +53,37 @@ struct stream_args {
   int64_t row_base;         // absolute index of the launch's first row (group_max indexing)
   int32_t rows, n_frames, n_filter, hop, nhalf, nstages, kpairs;
   int32_t total_frames, tile_frames, n_tiles, top_db_group;
-  int32_t n_a, n_b;         // ring depths: A pair-stages (producers -> MMA), DFT operand pair-stages (loader -> MMA)
 };
 
 struct smem_layout {
-  int samp, a_ring, b_ring, dw, dids, dctl, mid, gmax, us2, midp, e, bars, tmem_slot, total;
+  int samp, a_stage, b_stage, dw, dids, dctl, mid, gmax, us2, midp, bars, tmem_slot, total;
 };
 
-__host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpairs, int nfil, int n_a, int n_b) {
+__host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpairs) {
   smem_layout L;
   int off = 0;
   L.samp = off;      off += kMaxSlots * hop * 4;            // dense hop-block rows, 128-byte swizzled (base 1024-aligned)
   off = (off + 127) & ~127;
-  L.a_ring = off;    off += n_a * kAPairBytes;
-  L.b_ring = off;    off += n_b * fe_gemm_b_pair_bytes(nhalf);
+  L.a_stage = off;   off += 2 * kAStageBytes;
+  L.b_stage = off;   off += 2 * fe_gemm_b_stage_bytes(nhalf);
   L.dw = off;        off += (nhalf / 2 + 1) * (int)sizeof(fe_drain_w);
   L.dids = off;      off += (nhalf / 2 + 1) * (int)sizeof(fe_drain_ids);
   L.dctl = off;      off += ((nhalf / 8 + 1) * 4 + 15) & ~15;
-  L.mid = off;       off += kpairs * 4;          // weights of bin n_fft/4: [pass][j / 2] (even j -> Re, odd j -> Im)
+  L.mid = off;       off += kpairs * 4;          // interleaved weights of bin n_fft/4: even j -> Re, odd j -> Im
   L.gmax = off;      off += ((kMaxSlots + 1) * 4 + 15) & ~15;   // max |x| per hop block of the tile
-  L.us2 = off;       off += 2 * kTileM * 4;      // [tile parity][frame] unscale^2
-  L.midp = off;      off += 8 * kTileM * 4;      // [tile parity][pass][K half][frame] partial sums of bin n_fft/4
-  L.e = off;         off += FE_DRAIN_GROUPS * (nfil + 1) * kTileM * 4;   // emission scratch [group][filter + dummy][frame]
-  L.bars = off;      off += 32 * 8;
+  L.us2 = off;       off += kTileM * 4;
+  L.midp = off;      off += 4 * kTileM * 8;   // [producer half-group 2][K half 2][frame] (Re, Im) partials of bin n_fft/4
+  L.bars = off;      off += 16 * 8;
   L.tmem_slot = off; off += 16;
   L.total = off;
   return L;
 }
 
-enum {
-  BAR_SAMP_FULL = 0, BAR_SAMP_EMPTY = 1,
-  BAR_ACC_FULL = 4,            // +pass
-  BAR_ACC_EMPTY = 6,           // +pass
-  BAR_A_FULL = 8,              // +slot (kMaxRing)
-  BAR_A_FREE = 12,
-  BAR_B_FULL = 16,
-  BAR_B_FREE = 20,
-  BAR_COUNT = 24
-};
+enum { BAR_SAMP_FULL = 0, BAR_SAMP_EMPTY = 1, BAR_A_FULL = 2, BAR_B_FULL = 4, BAR_STAGE_FREE = 6, BAR_ACC_FULL = 8,
+       BAR_ACC_EMPTY = 9, BAR_SCOUT_FULL = 10, BAR_ZERO_DONE = 11, BAR_COUNT = 12 };
 
 #ifdef FE_GEMM_TRACE
-#define ST_TRACE(ev, it, q) do { if (blockIdx.x == 0 && (it) < 8) { ((long long*)(a.error_flag + 64))[((it) * 16 + (q)) * 16 + (ev)] = clock64(); } } while (0)
+#define ST_TRACE(ev, it, q) do { if (blockIdx.x == 0 && (it) < 8) { ((long long*)(a.error_flag + 64))[((it) * 8 + (q)) * 16 + (ev)] = clock64(); } } while (0)
 #else
 #define ST_TRACE(ev, it, q) do { } while (0)
 #endif
@@ -137,25 +127,17 @@ __device__ __forceinline__ void scout_rows(const unsigned char* s_samp, float* s
   }
 }
 
-__device__ __forceinline__ void drain_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kDrainThreads) : "memory"); }
-__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kProdWarps * 32) : "memory"); }
-
-// ring position: slot index and the parity of the slot's current use
-struct ring_pos {
-  uint32_t slot, par;
-  __device__ __forceinline__ void advance(uint32_t depth) {
-    if (++slot == depth) { slot = 0; par ^= 1u; }
-  }
-};
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_constant__ tmaps8 maps, const stream_args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const smem_layout L = make_layout(a.hop, a.nhalf, a.kpairs, a.n_filter, a.n_a, a.n_b);
+  const smem_layout L = make_layout(a.hop, a.nhalf, a.kpairs);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
   const int nF = a.n_frames, hop = a.hop, nfil = a.n_filter;
+  const int nbuf = h->gemm_nbuf;   // emission buffers of the drain (2 or 4)
   const int rs = hop * 4;        // bytes per hop-block row (dense; the 128-byte swizzle keeps lane <-> frame reads conflict-free)
 
   if (!h->gemm_ok) {
@@ -172,8 +154,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   float* s_mid = reinterpret_cast<float*>(smem + L.mid);
   float* s_gmax = reinterpret_cast<float*>(smem + L.gmax);
   float* s_us2 = reinterpret_cast<float*>(smem + L.us2);
-  float* s_midp = reinterpret_cast<float*>(smem + L.midp);
-  float* s_E = reinterpret_cast<float*>(smem + L.e);
+  float2* s_midp = reinterpret_cast<float2*>(smem + L.midp);
+  float* s_E = reinterpret_cast<float*>(smem + L.a_stage);   // drain scratch [nbuf][n_filter + 1][128] aliases the A slots (from slot 0 on)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const uint32_t bars = smem_u32(smem + L.bars);
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
@@ -187,9 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
     const uint32_t* gctl = reinterpret_cast<const uint32_t*>(blob + h->off_gemm_dctl);
     for (int i = tid; i <= a.nhalf / 8; i += kThreads) s_dctl[i] = gctl[i];
     const float* gmid = reinterpret_cast<const float*>(blob + h->off_gemm_mid);
-    // [pass][j / 2]: pass 0 = Re weights of the even sample pairs, pass 1 = Im weights of the odd ones
-    for (int i = tid; i < a.kpairs; i += kThreads) s_mid[(i & 1) * (a.kpairs / 2) + (i >> 1)] = (i & 1) ? gmid[a.kpairs + i] : gmid[i];
-    for (int i = tid; i < FE_DRAIN_GROUPS * (nfil + 1) * kTileM; i += kThreads) s_E[i] = 0.0f;
+    for (int i = tid; i < a.kpairs; i += kThreads) s_mid[i] = (i & 1) ? gmid[a.kpairs + i] : gmid[i];
     // rows a tile does not use are never read unpredicated, but keep the buffer defined
     float4* z = reinterpret_cast<float4*>(s_samp);
     for (int i = tid; i < kMaxSlots * rs / 16; i += kThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -197,17 +177,17 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   }
   if (tid == 0) {
     mbar_init(bar(BAR_SAMP_FULL), 2);
-    mbar_init(bar(BAR_SAMP_EMPTY), kProdWarps);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(bar(BAR_ACC_FULL + t), kNumMmaWarps);
-      mbar_init(bar(BAR_ACC_EMPTY + t), kDrainWarps);
-    }
-    for (int s = 0; s < kMaxRing; ++s) {
-      mbar_init(bar(BAR_A_FULL + s), kProdWarps);
-      mbar_init(bar(BAR_A_FREE + s), kNumMmaWarps);
-      mbar_init(bar(BAR_B_FULL + s), 1);
-      mbar_init(bar(BAR_B_FREE + s), kNumMmaWarps);
-    }
+    mbar_init(bar(BAR_SAMP_EMPTY), kWorkerWarps);
+    mbar_init(bar(BAR_A_FULL + 0), kWorkerWarps / 2);
+    mbar_init(bar(BAR_A_FULL + 1), kWorkerWarps / 2);
+    mbar_init(bar(BAR_B_FULL + 0), 1);
+    mbar_init(bar(BAR_B_FULL + 1), 1);
+    mbar_init(bar(BAR_STAGE_FREE + 0), kNumMmaWarps);
+    mbar_init(bar(BAR_STAGE_FREE + 1), kNumMmaWarps);
+    mbar_init(bar(BAR_ACC_FULL), kNumMmaWarps);
+    mbar_init(bar(BAR_ACC_EMPTY), 1);
+    mbar_init(bar(BAR_SCOUT_FULL), kNumMmaWarps);
+    mbar_init(bar(BAR_ZERO_DONE), kNumMmaWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp0) {
@@ -219,23 +199,23 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const int T = (int)a.T;
-  const uint32_t b_pair_bytes = (uint32_t)fe_gemm_b_pair_bytes(a.nhalf);
-  const uint32_t n_a = (uint32_t)a.n_a, n_b = (uint32_t)a.n_b;
+  const uint32_t b_stage_bytes = (uint32_t)fe_gemm_b_stage_bytes(a.nhalf);
 
-  if (warp == kSampLoaderWarp) {
-    // ================================ sample loader ===================================================
+  if (warp == kLoaderWarp) {
+    // ================================ loader ==========================================================
+    const unsigned char* gB = blob + h->off_gemm_b;
     const uint32_t row_bytes = (uint32_t)hop * 4u;
-    uint32_t it = 0;
+    uint32_t n = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
-      mbar_wait_relaxed(bar(BAR_SAMP_EMPTY), (it & 1u) ^ 1u, a.error_flag, 1);   // producers are done with the previous tile's samples
-      if (lane == 0) ST_TRACE(0, it, 0);
+      mbar_wait_relaxed(bar(BAR_SAMP_EMPTY), (it & 1u) ^ 1u, a.error_flag, 1);   // workers are done with the previous tile's samples
+      ST_TRACE(0, it, 0);
       int n_edge = 0;
       for (int row = g.row0; row <= g.row_last; ++row) {
         const int sa = row * (nF + 1) - g.sv0, sb = sa + nF;
         n_edge += (sa >= 0 && sa < g.nv) + (sb >= 0 && sb < g.nv);
       }
-      fence_proxy_async();   // earlier generic reads / writes of the buffer vs. the bulk copies below
+      fence_proxy_async();   // earlier generic writes of edge rows vs. the bulk copies below
       if (lane == 0) mbar_arrive_expect_tx(bar(BAR_SAMP_FULL), (uint32_t)(g.nv - n_edge) * row_bytes);
       __syncwarp();
       // per utterance segment: its ordinary hop blocks are contiguous; box heights = binary digits of their count
@@ -273,226 +253,221 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         }
       }
       __syncwarp();
+      if (lane == 0) ST_TRACE(9, it, 0);
       if (lane == 0) mbar_arrive(bar(BAR_SAMP_FULL));
-      if (lane == 0) ST_TRACE(1, it, 0);
-    }
-  } else if (warp == kOperandLoaderWarp) {
-    // ================================ DFT operand loader ==============================================
-    if (lane == 0) {
-      const unsigned char* gB = blob + h->off_gemm_b;
-      const uint32_t b_stage_bytes = (uint32_t)fe_gemm_b_stage_bytes(a.nhalf);
-      ring_pos rb{0u, 0u};
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        for (int t = 0; t < 2; ++t) {
-          for (int q = 0; q < a.nstages; ++q) {
-            mbar_wait_relaxed(bar(BAR_B_FREE + rb.slot), rb.par ^ 1u, a.error_flag, 2);   // the MMAs that read the slot have retired
-            mbar_arrive_expect_tx(bar(BAR_B_FULL + rb.slot), b_pair_bytes);
-            bulk_g2s(smem_u32(smem + L.b_ring + rb.slot * b_pair_bytes),
-                     gB + (size_t)q * b_stage_bytes + (size_t)t * b_pair_bytes, b_pair_bytes, bar(BAR_B_FULL + rb.slot));
-            rb.advance(n_b);
-          }
+      if (lane == 0) {
+        for (int q = 0; q < a.nstages; ++q, ++n) {
+          const uint32_t s = n & 1u, par = (n >> 1) & 1u;
+          mbar_wait_relaxed(bar(BAR_STAGE_FREE + s), par ^ 1u, a.error_flag, 2);   // the MMAs that read slot s have retired
+          mbar_arrive_expect_tx(bar(BAR_B_FULL + s), b_stage_bytes);
+          bulk_g2s(smem_u32(smem + L.b_stage + s * b_stage_bytes), gB + (size_t)q * b_stage_bytes, b_stage_bytes,
+                   bar(BAR_B_FULL + s));
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp >= kMmaWarp0) {
     // ================================ MMA issuers =====================================================
-    // One issuing warp per sub-GEMM of the pass's pair (own accumulator).  Everything the issuing thread needs is
-    // derived from warp-uniform values (shuffle broadcasts, kernel parameters) and the MMAs sit under elect.sync,
-    // so the descriptors live in uniform registers and no per-lane "waterfall" loop is generated around each
-    // UTCHMMA (tests/cuda/ts_probe.cu).
-    const int sub = __shfl_sync(0xffffffffu, warp - kMmaWarp0, 0);
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(a.nhalf >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    const uint32_t b_lbo = (uint32_t)a.nhalf * 16u;
-    const uint32_t smem_a = smem_u32(smem + L.a_ring), smem_b = smem_u32(smem + L.b_ring);
-    const uint32_t tile_bytes_a = fe_gemm_tile_bytes(kTileM), tile_bytes_b = fe_gemm_tile_bytes(a.nhalf);
-    ring_pos ra{0u, 0u}, rb{0u, 0u};
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait_relaxed(bar(BAR_ACC_EMPTY + t), (it & 1u) ^ 1u, a.error_flag, 3);   // the previous tile's pass t is drained
+    // A lone thread issues one tcgen05.mma per ~100 cycles (dependent uniform-datapath instructions around every
+    // UTCHMMA; measured with tests/cuda/ts_probe.cu), slower than the tensor pipe retires an N = 128 MMA (64
+    // cycles).  The four sub-GEMMs own separate accumulators, so each gets its own issuing warp.
+    // Everything the issuing thread needs is derived from warp-uniform values (shuffle broadcasts, kernel
+    // parameters) and the MMAs sit under elect.sync, so the descriptors live in uniform registers and no per-lane
+    // "waterfall" loop is generated around each UTCHMMA (that loop made one thread issue only one MMA per ~100
+    // cycles, slower than the tensor pipe retires them: tests/cuda/ts_probe.cu).
+    {
+      const int sub0 = (4 / kNumMmaWarps) * __shfl_sync(0xffffffffu, warp - kMmaWarp0, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(a.nhalf >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t b_lbo = (uint32_t)a.nhalf * 16u;
+      const uint32_t smem_a = smem_u32(smem + L.a_stage), smem_b = smem_u32(smem + L.b_stage);
+      const uint32_t tile_bytes_a = fe_gemm_tile_bytes(kTileM), tile_bytes_b = fe_gemm_tile_bytes(a.nhalf);
+      uint32_t n = 0, it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        // scout: this tile's samples land while the workers still drain the previous tile; these warps are idle then
+        {
+          const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
+          mbar_wait_relaxed(bar(BAR_SAMP_FULL), it & 1u, a.error_flag, 10);
+          scout_rows(s_samp, s_gmax, rs, g.nv, warp - kMmaWarp0, kNumMmaWarps, lane);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL));
+        }
+        mbar_wait_relaxed(bar(BAR_ACC_EMPTY), (it & 1u) ^ 1u, a.error_flag, 3);   // previous tile drained
         tc_fence_after();
-        const uint32_t d_tmem = tmem_u + (uint32_t)((2 * t + sub) * a.nhalf);
-        for (int q = 0; q < a.nstages; ++q) {
-          mbar_wait_relaxed(bar(BAR_B_FULL + rb.slot), rb.par, a.error_flag, 4);
-          mbar_wait_relaxed(bar(BAR_A_FULL + ra.slot), ra.par, a.error_flag, 5);
+        for (int q = 0; q < a.nstages; ++q, ++n) {
+          const uint32_t s = n & 1u, par = (n >> 1) & 1u;
+          mbar_wait_relaxed(bar(BAR_B_FULL + s), par, a.error_flag, 4);
+          mbar_wait_relaxed(bar(BAR_A_FULL + s), par, a.error_flag, 5);
           tc_fence_after();
-          if (sub == 0 && lane == 0) ST_TRACE(3, it, t * 5 + q);
-          const uint32_t a_base = smem_a + ra.slot * kAPairBytes + (uint32_t)(2 * sub) * tile_bytes_a;
-          const uint32_t b_base = smem_b + rb.slot * b_pair_bytes + (uint32_t)(2 * sub) * tile_bytes_b;
+          if (sub0 == 0 && lane == 0) ST_TRACE(3, it, q);
+          const uint32_t a_base = smem_a + s * kAStageBytes;
+          const uint32_t b_base = smem_b + s * b_stage_bytes;
           if (elect_one()) {
-            // A_hi B_hi + A_lo B_hi + A_hi B_lo
+            // this warp's sub-GEMM(s): A_hi B_hi + A_lo B_hi + A_hi B_lo, alternating accumulators if it has two
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr) {
-              const uint64_t da = make_desc(a_base + (pr == 1 ? tile_bytes_a : 0u), kTileM * 16, 128);
-              const uint64_t db = make_desc(b_base + (pr == 2 ? tile_bytes_b : 0u), b_lbo, 128);
-              umma_f16(d_tmem, da, db, idesc, (q > 0 || pr > 0) ? 1u : 0u);
+#pragma unroll
+              for (int ds = 0; ds < 4 / kNumMmaWarps; ++ds) {
+                const int sub = sub0 + ds;
+                const uint64_t da = make_desc(a_base + (2 * sub + (pr == 1 ? 1 : 0)) * tile_bytes_a, kTileM * 16, 128);
+                const uint64_t db = make_desc(b_base + (2 * sub + (pr == 2 ? 1 : 0)) * tile_bytes_b, b_lbo, 128);
+                umma_f16(tmem_u + (uint32_t)(sub * a.nhalf), da, db, idesc, (q > 0 || pr > 0) ? 1u : 0u);
+              }
             }
-            umma_commit(bar(BAR_A_FREE + ra.slot));
-            umma_commit(bar(BAR_B_FREE + rb.slot));
-            if (q == a.nstages - 1) umma_commit(bar(BAR_ACC_FULL + t));
+            umma_commit(bar(BAR_STAGE_FREE + s));
+            if (q == a.nstages - 1) umma_commit(bar(BAR_ACC_FULL));
           }
           __syncwarp();
-          ra.advance(n_a);
-          rb.advance(n_b);
         }
+        // the drain scratch aliases A slot 0: clear it as soon as the tile's MMAs (its last readers) have retired,
+        // while the workers already load their first accumulator columns
+        mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 11);
+        {
+          float4* z = reinterpret_cast<float4*>(s_E);
+          for (int i = (warp - kMmaWarp0) * 32 + lane; i < nbuf * (nfil + 1) * kTileM / 4; i += kNumMmaWarps * 32)
+            z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_ZERO_DONE));
       }
     }
-  } else if (warp >= kProdWarp0) {
-    // ================================ producers (warps 8..15) =========================================
-    const int pw = warp - kProdWarp0;
-    const int khalf = pw >> 2;               // which 16 of the pair-stage's 32 sample pairs = which K chunk of 8
-    const int m = (pw & 3) * 32 + lane;      // frame of the tile
-    ring_pos ra{0u, 0u};
-    uint32_t it = 0;
+  } else {
+    // ================================ workers (warps 0..15) ===========================================
+    const int quarter = warp & 3;          // TMEM lane quarter (drain) = frame quarter (production)
+    const int khalf = (warp >> 2) & 1;     // production: which 16 of the stage's 32 sample pairs
+    const int pgrp = warp >> 3;            // production: stages with (n & 1) == pgrp, i.e. A slot pgrp
+    const int cg = warp >> 2;              // drain: column group
+    const int m = quarter * 32 + lane;
+    const int cpg = a.nhalf / FE_DRAIN_GROUPS;
+    uint32_t n = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
       const int mm = min(m, g.count - 1);                 // rows past the end of the stream repeat the last frame
       const int row = (g.g0 + mm) / nF;
       const int slot = mm + (row - g.row0);               // backward hop block; the forward one is slot + 1
       mbar_wait(bar(BAR_SAMP_FULL), it & 1u, a.error_flag, 6);
-      // scout: max |x| of every hop block of the tile (all eight warps, four rows per warp step), then everybody reads
-      scout_rows(s_samp, s_gmax, rs, g.nv, pw, kProdWarps, lane);
-      prod_bar();
-      if (tid == kProdWarp0 * 32) ST_TRACE(2, it, 0);
+      if (tid == 0) ST_TRACE(1, it, 0);
+      // the MMA warps have scouted the tile's hop blocks (max |x| each) while these warps drained the previous one
+      mbar_wait(bar(BAR_SCOUT_FULL), it & 1u, a.error_flag, 9);
+      worker_bar();
+      if (tid == 0) ST_TRACE(7, it, 0);
       float scale, unscale;
       fe_gemm_frame_scale(2.0f * fmaxf(s_gmax[slot], s_gmax[slot + 1]), scale, unscale);
-      if (khalf == 0) s_us2[(it & 1u) * kTileM + m] = unscale * unscale;
+      // ---- produce
       const uint32_t brow = (uint32_t)(slot * rs), frow = brow + (uint32_t)rs;   // byte offsets into the sample buffer
-      // A unit's 16 forward samples (and its 16 backward ones) are a 64-byte aligned span inside ONE 128-byte line of
-      // the swizzled buffer: one swizzle term per span, chunk address = line | ((offset in line) ^ term).
-      const uint32_t samp_base = smem_u32(s_samp);
-      const uint32_t fc = 64u * (uint32_t)khalf, bc = 64u - fc;   // span offsets inside their lines (hop * 4 is a multiple of 128)
+      float mid_re = 0.0f, mid_im = 0.0f;
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        float mid = 0.0f;
-        const float* midw = s_mid + t * (a.kpairs / 2) + 8 * khalf;
-#pragma unroll 1
-        for (int q = 0; q < a.nstages; ++q) {
-          const int j0 = 32 * q + 16 * khalf;
-          const uint32_t fline = (frow + (uint32_t)j0 * 4u) & ~127u, bline = (brow + (uint32_t)(hop - j0 - 16) * 4u) & ~127u;
-          const uint32_t fx = ((fline >> 7) & 7u) << 4, bx = ((bline >> 7) & 7u) << 4;
-          float fwd[16], bwd[16], buf[16];
+      for (int q = 0; q < a.nstages; ++q, ++n) {
+        if ((int)(n & 1u) != pgrp) continue;
+        const uint32_t par = (n >> 1) & 1u;
+        const int j0 = 32 * q + 16 * khalf;
+        float fwd[16], bwd[16], buf[16];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            float4 f, b;   // asm: keeps the 16-byte loads whole even where only three of their elements are used
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
-                         : "r"(samp_base + (fline | ((fc + 16u * ch) ^ fx))));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                         : "r"(samp_base + (bline | ((bc + 16u * ch) ^ bx))));
-            fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
-            buf[4 * ch + 0] = b.x; buf[4 * ch + 1] = b.y; buf[4 * ch + 2] = b.z; buf[4 * ch + 3] = b.w;
-          }
-          // bwd[i] = x[c - j0 - i] = backward-row element hop - j0 - i; element hop (i = 0, j0 = 0) is the centre sample
-          bwd[0] = (j0 == 0) ? fwd[0] : *reinterpret_cast<const float*>(s_samp + swz(brow + (hop - j0) * 4));
-#pragma unroll
-          for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
-          fe_u4 chunk[4];
-          if (t == 0) fe_stream_produce_unit<0>(fwd, bwd, scale, midw + 16 * q, mid, chunk);
-          else fe_stream_produce_unit<1>(fwd, bwd, scale, midw + 16 * q, mid, chunk);
-          mbar_wait(bar(BAR_A_FREE + ra.slot), ra.par ^ 1u, a.error_flag, 7);   // MMAs of the slot's previous use retired
-          if (tid == kProdWarp0 * 32) ST_TRACE(11, it, t * 5 + q);
-          unsigned char* a_row = smem + L.a_ring + ra.slot * kAPairBytes + khalf * kTileM * 16 + m * 16;
-#pragma unroll
-          for (int sf = 0; sf < 4; ++sf) *reinterpret_cast<fe_u4*>(a_row + sf * fe_gemm_tile_bytes(kTileM)) = chunk[sf];
-          if (q == a.nstages - 1) s_midp[(((it & 1u) * 2 + t) * 2 + khalf) * kTileM + m] = mid;   // before the arrive below
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_A_FULL + ra.slot));
-          if (tid == kProdWarp0 * 32) ST_TRACE(10, it, t * 5 + q);
-          ra.advance(n_a);
+        for (int ch = 0; ch < 4; ++ch) {
+          const float4 f = *reinterpret_cast<const float4*>(s_samp + swz(frow + j0 * 4 + ch * 16));
+          fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
+          float4 b;   // asm: keeps the 16-byte load whole even where only three of its elements are used
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                       : "r"(smem_u32(s_samp) + swz(brow + (hop - j0 - 16) * 4 + ch * 16)));
+          buf[4 * ch + 0] = b.x; buf[4 * ch + 1] = b.y; buf[4 * ch + 2] = b.z; buf[4 * ch + 3] = b.w;
         }
+        // bwd[i] = x[c - j0 - i] = backward-row element hop - j0 - i; element hop (i = 0, j0 = 0) is the centre sample
+        bwd[0] = (j0 == 0) ? fwd[0] : *reinterpret_cast<const float*>(s_samp + swz(brow + (hop - j0) * 4));
+#pragma unroll
+        for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
+        fe_u4 chunk[8];
+        fe_stream_produce_unit(fwd, bwd, scale, s_mid + j0, mid_re, mid_im, chunk);
+        mbar_wait(bar(BAR_STAGE_FREE + pgrp), par ^ 1u, a.error_flag, 7);   // MMAs of this slot's previous use retired
+        unsigned char* a_row = smem + L.a_stage + pgrp * kAStageBytes + khalf * kTileM * 16 + m * 16;
+#pragma unroll
+        for (int sf = 0; sf < 8; ++sf) *reinterpret_cast<fe_u4*>(a_row + sf * fe_gemm_tile_bytes(kTileM)) = chunk[sf];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_A_FULL + pgrp));
+        if (tid == 0 || tid == 256) ST_TRACE(2, it, q);
       }
+      // partial sums are filed by stage parity (even stages / odd stages), not by warp group: the groups swap
+      // stage sets from tile to tile, and the drain's summation order must not depend on the tile index
+      s_midp[((int)((n ^ (uint32_t)pgrp ^ (uint32_t)a.nstages) & 1u) * 2 + khalf) * kTileM + m] = make_float2(mid_re, mid_im);
+      if (pgrp == 0 && khalf == 0) s_us2[m] = unscale * unscale;
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_SAMP_EMPTY));   // every read of the tile's samples is done
-      if (tid == kProdWarp0 * 32) ST_TRACE(4, it, 0);
-    }
-  } else {
-    // ================================ drain (warps 0..7) ==============================================
-    const int quarter = warp & 3;          // TMEM lane quarter
-    const int cg = warp >> 2;              // column group
-    const int m = quarter * 32 + lane;
-    const int cpg = a.nhalf / FE_DRAIN_GROUPS;
-    float* e_col = s_E + cg * (nfil + 1) * kTileM + m;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
-#pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait(bar(BAR_ACC_FULL + t), it & 1u, a.error_flag, 8);
-        tc_fence_after();
-        if (tid == 0) ST_TRACE(5 + t, it, 0);
+      if (lane == 0) mbar_arrive(bar(BAR_SAMP_EMPTY));
+      // ---- drain
+      mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 8);
+      tc_fence_after();
+      worker_bar();   // every worker's s_midp / s_us2 entries of the tile are written before any drain thread reads them
+      if (tid == 0) ST_TRACE(4, it, 0);
+      {
         fe_drain_state st;
         fe_drain_init(st, s_dids[(cg * cpg) >> 1]);   // aimed at the filters of the group's first pair
-        const float us2 = s_us2[(it & 1u) * kTileM + m];
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * t * a.nhalf);
+        float* e_col = s_E + (cg & (nbuf - 1)) * (nfil + 1) * kTileM + m;
+        const float us2 = s_us2[m];
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int k_begin = cg * cpg;
+        bool scratch_ready = false;
 #pragma unroll 1
         for (int k0 = k_begin; k0 < k_begin + cpg; k0 += 8) {
-          float u[8], v[8];
-          tmem_ld8(tbase + (uint32_t)k0, u);
-          tmem_ld8(tbase + (uint32_t)(a.nhalf + k0), v);
-          // the batch's weights and switch word travel while the accumulators are fetched
-          fe_drain_w wt[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) wt[p] = s_dw[(k0 >> 1) + p];
+          float ce[8], co[8], se[8], so[8];
+          tmem_ld8(tbase + (uint32_t)(0 * a.nhalf + k0), ce);
+          tmem_ld8(tbase + (uint32_t)(1 * a.nhalf + k0), co);
+          tmem_ld8(tbase + (uint32_t)(2 * a.nhalf + k0), se);
+          tmem_ld8(tbase + (uint32_t)(3 * a.nhalf + k0), so);
           const unsigned ctl = s_dctl[k0 >> 3];
+          if (!scratch_ready) {   // the MMA warps clear the emission scratch while the first columns are being loaded
+            mbar_wait(bar(BAR_ZERO_DONE), it & 1u, a.error_flag, 12);
+            scratch_ready = true;
+          }
           tmem_ld_wait();
-          tmem_ld_tie8(u); tmem_ld_tie8(v);
-          if (tid == 0) ST_TRACE(12, it, t * 8 + ((k0 - k_begin) >> 3));
-          fe_drain_pairs<4>(wt, s_dids + (k0 >> 1), ctl, u, v, st, e_col, us2);
-          if (tid == 0) ST_TRACE(13, it, t * 8 + ((k0 - k_begin) >> 3));
+          tmem_ld_tie8(ce); tmem_ld_tie8(co); tmem_ld_tie8(se); tmem_ld_tie8(so);
+          fe_drain_pairs<4>(s_dw + (k0 >> 1), s_dids + (k0 >> 1), ctl, ce, co, se, so, st, e_col, us2);
         }
         if (cg == FE_DRAIN_GROUPS - 1) {
           // bin n_fft/4 from the producers' partial sums (scaled sample units -> accumulator units: x 2^14)
-          const float* mp = s_midp + (((it & 1u) * 2 + t) * 2) * kTileM + m;
-          const float part = (mp[0] + mp[kTileM]) * (float)(1 << FE_GEMM_B_SCALE_LOG2);
-          fe_drain_mid(s_dw + a.nhalf / 2, s_dids + a.nhalf / 2, s_dctl[a.nhalf >> 3], part * part, st, e_col, us2);
+          float re = 0.0f, im = 0.0f;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) { const float2 v = s_midp[p * kTileM + m]; re += v.x; im += v.y; }
+          const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
+          re *= bs; im *= bs;
+          fe_drain_mid(s_dw + a.nhalf / 2, s_dids + a.nhalf / 2, s_dctl[a.nhalf >> 3], fmaf(re, re, im * im), st, e_col, us2);
         }
         fe_drain_flush(st, e_col, us2);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + t));   // this half of TMEM is free for the next tile's pass t
-        if (tid == 0) ST_TRACE(7 + t, it, 0);
+        if (tid == 0) ST_TRACE(12, it, 0);
+      }
+      tc_fence_before();
+      worker_bar();
+      if (tid == 0) {
+        mbar_arrive(bar(BAR_ACC_EMPTY));   // TMEM is free for the next tile's MMAs
+        ST_TRACE(5, it, 0);
       }
       // ---- finalize: this tile's energies -> workspace, per-group maximum
-      drain_bar();   // both groups' emissions of both passes are in the scratch
       {
-        const int mm = min(m, g.count - 1);
-        const int row = (g.g0 + mm) / nF;
         const int t = (g.g0 + mm) - row * nF;
         const bool valid = m < g.count;
         float* dst = a.energies + (size_t)row * nfil * nF + t;
         float vmax = 0.0f;
-        // thread -> frame m, filters f = cg + 2 u: all shared-memory reads first (and the scratch cleared for the
-        // next tile), then the stores
+        // thread -> frame m, filters f = (warp >> 2) + 4 u: all shared-memory reads first, then the stores
         const int bsz = (nfil + 1) * kTileM;   // buffer stride (the last row of each buffer is the dummy row)
-        float v[FE_GEMM_MAX_FILTERS / FE_DRAIN_GROUPS];
+        float v[FE_GEMM_MAX_FILTERS / 4];
 #pragma unroll
-        for (int u = 0; u < FE_GEMM_MAX_FILTERS / FE_DRAIN_GROUPS; ++u) {
-          const int f = cg + FE_DRAIN_GROUPS * u;
+        for (int u = 0; u < FE_GEMM_MAX_FILTERS / 4; ++u) {
+          const int f = (warp >> 2) + 4 * u;
           v[u] = 0.0f;
           if (f < nfil) {
-            float sum = 0.0f;
-#pragma unroll
-            for (int b = 0; b < FE_DRAIN_GROUPS; ++b) {
-              sum += s_E[b * bsz + f * kTileM + m];
-              s_E[b * bsz + f * kTileM + m] = 0.0f;
-            }
-            v[u] = sum;
+            v[u] = s_E[f * kTileM + m] + s_E[bsz + f * kTileM + m];
+            if (nbuf == 4) v[u] += s_E[2 * bsz + f * kTileM + m] + s_E[3 * bsz + f * kTileM + m];
           }
         }
         if (valid) {
-          float* o = dst + (size_t)cg * nF;
+          float* o = dst + (size_t)(warp >> 2) * nF;
 #pragma unroll
-          for (int u = 0; u < FE_GEMM_MAX_FILTERS / FE_DRAIN_GROUPS; ++u, o += FE_DRAIN_GROUPS * (size_t)nF) {
-            if (cg + FE_DRAIN_GROUPS * u < nfil) {
+          for (int u = 0; u < FE_GEMM_MAX_FILTERS / 4; ++u, o += 4 * (size_t)nF) {
+            if ((warp >> 2) + 4 * u < nfil) {
               *o = v[u];
               vmax = fmaxf(vmax, v[u]);
             }
           }
         }
+        if (tid == 0) ST_TRACE(13, it, 0);
         if (a.group_max) {
           const int grp_id = (int)((a.row_base + row) / a.top_db_group);
           const int grp0 = __shfl_sync(0xffffffffu, grp_id, 0);
@@ -505,8 +480,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           }
         }
       }
-      drain_bar();   // the scratch is clear before anyone emits the next tile into it
-      if (tid == 0) ST_TRACE(9, it, 0);
+      if (tid == 0) ST_TRACE(6, it, 0);
+      // (the next tile's scout barrier separates these reads of s_E from the next production's A stores)
     }
   }
 
@@ -537,19 +512,6 @@ encode_tiled_fn get_encode() {
   return fn;
 }
 
-// ring depths: the deepest pair (A slots, DFT operand slots) that fits the 227 KB of shared memory
-bool pick_rings(int hop, int nhalf, int kpairs, int nfil, int* n_a, int* n_b) {
-  static const int cand[][2] = {{4, 3}, {3, 3}, {3, 2}, {2, 2}};
-  for (const auto& c : cand) {
-    if (make_layout(hop, nhalf, kpairs, nfil, c[0], c[1]).total <= 227 * 1024) {
-      *n_a = c[0];
-      *n_b = c[1];
-      return true;
-    }
-  }
-  return false;
-}
-
 }  // namespace
 
 int32_t fe_gemm_compiled(void) { return 1; }
@@ -559,9 +521,8 @@ bool fe_gemm_supported(const b200fe_params* p) {
   if (p->win_length != 2 * p->hop_length || p->win_length > p->n_fft) return false;
   const int kpairs = p->win_length / 2, nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return false;
-  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return false;   // 2 passes x 2 accumulators fit TMEM
-  int n_a, n_b;
-  return pick_rings(p->hop_length, nhalf, kpairs, p->n_filter, &n_a, &n_b);
+  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return false;   // 4 accumulators fit TMEM
+  return make_layout(p->hop_length, nhalf, kpairs).total <= 227 * 1024;
 }
 
 bool fe_gemm_preferred(const b200fe_params* p) {
@@ -608,7 +569,6 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
   a.tile_frames = fe_tile_frames(fa.n_frames);
   a.n_tiles = (a.total_frames + a.tile_frames - 1) / a.tile_frames;
   a.top_db_group = fa.top_db_group;
-  if (!pick_rings(a.hop, a.nhalf, a.kpairs, a.n_filter, &a.n_a, &a.n_b)) return cudaErrorInvalidConfiguration;
 
   // 4-D tensor maps over the launch's rows: {32 floats, hop/32, ordinary hop blocks of a row, rows}, boxes of 2^k blocks
   encode_tiled_fn enc = get_encode();
@@ -626,7 +586,8 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
       if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     }
   }
-  const int smem = make_layout(a.hop, a.nhalf, a.kpairs, a.n_filter, a.n_a, a.n_b).total;
+  const int smem = make_layout(a.hop, a.nhalf, a.kpairs).total;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   const int dev = fe_current_device();
   if (dev < 0) return cudaErrorInvalidDevice;
   {

@@ -1,5 +1,5 @@
 """FE_GEMM_TRACE build only (make LIBDIR=../lib_trace EXTRA_NVFLAGS=-DFE_GEMM_TRACE; B200FE_LIB=...): SM-clock
-timeline of CTA 0 of the streaming kernel (two passes per tile, role-specialised warps)."""
+timeline of CTA 0 of the streaming kernel."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,14 +18,11 @@ ws = eng._workspace[x.device]
 nbytes = eng.lib.b200fe_workspace_bytes(C.byref(eng.params), R, 64600)
 tail = ws[nbytes - 65536: nbytes].cpu().numpy()
 print("flag", tail[:4].view(np.int32)[0])
-tr = np.frombuffer(tail[256:256 + 8 * 16 * 16 * 8].tobytes(), dtype=np.int64).reshape(8, 16, 16)
-base = tr[1, 0, 0]
-for it in range(1, 7):
+tr = np.frombuffer(tail[256:256 + 8 * 8 * 16 * 8].tobytes(), dtype=np.int64).reshape(8, 8, 16)
+base = tr[0, 0, 0]
+for it in range(7):
     r = lambda q, e: int(tr[it, q, e] - base)
-    print("tile", it, "loader_start", r(0, 0), "samples_issued", r(0, 1), "producers_start", r(0, 2), "producers_end", r(0, 4),
-          "| drain pass0", (r(0, 5), r(0, 7)), "pass1", (r(0, 6), r(0, 8)), "finalize_done", r(0, 9))
-    print("    slot_free(stage):", [r(q, 11) for q in range(10)])
-    print("    produced(stage): ", [r(q, 10) for q in range(10)])
-    print("    mma_issue(stage):", [r(q, 3) for q in range(10)])
-    print("    drain batches pass0 (loaded, done):", [(r(b, 12), r(b, 13)) for b in range(8)])
-    print("    drain batches pass1 (loaded, done):", [(r(8 + b, 12), r(8 + b, 13)) for b in range(8)])
+    print("tile", it, "loader_start", r(0, 0), "samp_full", r(0, 1), "acc_full", r(0, 4), "drain_done", r(0, 5), "fin_done", r(0, 6),
+          "scout_done", r(0, 7), "fin_stores_done", r(0, 13), "edges_done", r(0, 9))
+    print("    drain batches (ld done, cols done):", [(r(b, 10), r(b, 11)) for b in range(4)], "flush", r(0, 12))
+    print("    produced(q):", [r(q, 2) for q in range(5)], " mma_issue(q):", [r(q, 3) for q in range(5)])

@@ -145,14 +145,14 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
   const float* gmid = (const float*)(blob + h->off_gemm_mid);
   const unsigned char* gB = blob + h->off_gemm_b;
   const int M = FE_GEMM_TILE_M;
-  // weights of bin n_fft/4 as the kernel lays them out in shared memory: [pass][j / 2], pass 0 = Re from even j, pass 1 = Im from odd j
-  std::vector<float> midw(kpairs);
-  for (int j = 0; j < kpairs; ++j) midw[(j & 1) * (kpairs / 2) + (j >> 1)] = (j & 1) ? gmid[kpairs + j] : gmid[j];
+  std::vector<float> midc(kpairs);   // interleaved weights of bin n_fft/4, as the kernel builds them in shared memory
+  for (int j = 0; j < kpairs; ++j) midc[j] = (j & 1) ? gmid[kpairs + j] : gmid[j];
 
   const int total = (int)(R * nF), tf = fe_tile_frames(nF);
   const int n_tiles = (total + tf - 1) / tf;
-  std::vector<unsigned char> a_pair(fe_gemm_a_pair_bytes());
-  std::vector<float> D((size_t)2 * M * nhalf), E((size_t)FE_DRAIN_GROUPS * (FE_GEMM_MAX_FILTERS + 1) * M);
+  std::vector<unsigned char> a_stage(fe_gemm_a_stage_bytes());
+  std::vector<float> D((size_t)4 * M * nhalf), E((size_t)4 * (FE_GEMM_MAX_FILTERS + 1) * M);
+  const int nbuf = h->gemm_nbuf;
   std::vector<float> samp, bmax;
   for (int tile = 0; tile < n_tiles; ++tile) {
     const fe_tile_geo g = fe_tile_geometry(tile, tf, total, nF);
@@ -172,8 +172,9 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
         bmax[s] = fmaxf(bmax[s], fabsf(val));   // scout
       }
     }
+    std::fill(D.begin(), D.end(), 0.0f);
     std::fill(E.begin(), E.end(), 0.0f);
-    std::vector<float> scale(M), unscale(M);
+    std::vector<float> scale(M), unscale(M), mre(M, 0.0f), mim(M, 0.0f);
     std::vector<int> slot(M);
     for (int m = 0; m < M; ++m) {
       const int mm = m < g.count ? m : g.count - 1;
@@ -181,67 +182,63 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
       slot[m] = mm + (row - g.row0);
       fe_gemm_frame_scale(2.0f * fmaxf(bmax[slot[m]], bmax[slot[m] + 1]), scale[m], unscale[m]);
     }
-    for (int pass = 0; pass < 2; ++pass) {
-      std::fill(D.begin(), D.end(), 0.0f);
-      std::vector<float> midp((size_t)2 * M, 0.0f);   // [khalf][frame]: partial sums of bin n_fft/4 (this pass's part)
-      for (int q = 0; q < nstages; ++q) {
-        // producers: thread (m, khalf)
-        for (int m = 0; m < M; ++m) {
-          const float* brow = samp.data() + (size_t)slot[m] * hop;
-          const float* frow = brow + hop;
-          for (int khalf = 0; khalf < 2; ++khalf) {
-            const int j0 = 32 * q + 16 * khalf;
-            float fwd[16], bwd[16];
-            for (int i = 0; i < 16; ++i) fwd[i] = frow[j0 + i];
-            bwd[0] = (j0 == 0) ? fwd[0] : brow[hop - j0];
-            for (int i = 1; i < 16; ++i) bwd[i] = brow[hop - j0 - i];
-            fe_u4 chunk[4];
-            const float* mw = midw.data() + pass * (kpairs / 2) + j0 / 2;
-            if (pass == 0) fe_stream_produce_unit<0>(fwd, bwd, scale[m], mw, midp[(size_t)khalf * M + m], chunk);
-            else fe_stream_produce_unit<1>(fwd, bwd, scale[m], mw, midp[(size_t)khalf * M + m], chunk);
-            for (int sf = 0; sf < 4; ++sf)
-              memcpy(a_pair.data() + sf * fe_gemm_tile_bytes(M) + fe_gemm_operand_offset(M, m, 8 * khalf), &chunk[sf], 16);
-          }
-        }
-        // "tcgen05.mma": D_sub += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo over the pair-stage's 16 K values
-        const unsigned char* b_pair = gB + (size_t)q * fe_gemm_b_stage_bytes(nhalf) + (size_t)pass * fe_gemm_b_pair_bytes(nhalf);
-        for (int sub = 0; sub < 2; ++sub)
-          for (int m = 0; m < M; ++m)
-            for (int n = 0; n < nhalf; ++n) {
-              float acc = D[((size_t)sub * M + m) * nhalf + n];
-              for (int kk = 0; kk < 16; ++kk) {
-                const float ah = emu_half_at(a_pair.data(), fe_gemm_a_tile_offset(sub, 0) + fe_gemm_operand_offset(M, m, kk));
-                const float al = emu_half_at(a_pair.data(), fe_gemm_a_tile_offset(sub, 1) + fe_gemm_operand_offset(M, m, kk));
-                const float bh = emu_half_at(b_pair, fe_gemm_b_tile_offset(nhalf, sub, 0) + fe_gemm_operand_offset(nhalf, n, kk));
-                const float bl = emu_half_at(b_pair, fe_gemm_b_tile_offset(nhalf, sub, 1) + fe_gemm_operand_offset(nhalf, n, kk));
-                acc += ah * bh + al * bh + ah * bl;
-              }
-              D[((size_t)sub * M + m) * nhalf + n] = acc;
-            }
-      }
-      // drain of this pass: thread (frame m, column group cg); one emission buffer per group
-      const int cpg = nhalf / FE_DRAIN_GROUPS;
+    for (int q = 0; q < nstages; ++q) {
+      // producers: thread (m, khalf)
       for (int m = 0; m < M; ++m) {
-        const float us2 = unscale[m] * unscale[m];
-        for (int cg = 0; cg < FE_DRAIN_GROUPS; ++cg) {
-          fe_drain_state st;
-          fe_drain_init(st, dids[cg * cpg / 2]);
-          float* e_col = E.data() + (size_t)cg * (nfil + 1) * M + m;
-          for (int k0 = cg * cpg; k0 < (cg + 1) * cpg; k0 += 8) {
-            float u[8], v[8];
-            for (int i = 0; i < 8; ++i) {
-              u[i] = D[((size_t)0 * M + m) * nhalf + k0 + i];
-              v[i] = D[((size_t)1 * M + m) * nhalf + k0 + i];
-            }
-            fe_drain_pairs<4>(dw + k0 / 2, dids + k0 / 2, dctl[k0 >> 3], u, v, st, e_col, us2);
-          }
-          if (cg == FE_DRAIN_GROUPS - 1) {
-            const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
-            const float part = (midp[m] + midp[(size_t)M + m]) * bs;
-            fe_drain_mid(dw + nhalf / 2, dids + nhalf / 2, dctl[nhalf >> 3], part * part, st, e_col, us2);
-          }
-          fe_drain_flush(st, e_col, us2);
+        const float* brow = samp.data() + (size_t)slot[m] * hop;
+        const float* frow = brow + hop;
+        for (int khalf = 0; khalf < 2; ++khalf) {
+          const int j0 = 32 * q + 16 * khalf;
+          float fwd[16], bwd[16];
+          for (int i = 0; i < 16; ++i) fwd[i] = frow[j0 + i];
+          bwd[0] = (j0 == 0) ? fwd[0] : brow[hop - j0];
+          for (int i = 1; i < 16; ++i) bwd[i] = brow[hop - j0 - i];
+          fe_u4 chunk[8];
+          fe_stream_produce_unit(fwd, bwd, scale[m], midc.data() + j0, mre[m], mim[m], chunk);
+          for (int sf = 0; sf < 8; ++sf)
+            memcpy(a_stage.data() + sf * fe_gemm_tile_bytes(M) + fe_gemm_operand_offset(M, m, 8 * khalf), &chunk[sf], 16);
         }
+      }
+      // "tcgen05.mma": D_sub += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo over the stage's 16 K values
+      const unsigned char* b_stage = gB + (size_t)q * fe_gemm_b_stage_bytes(nhalf);
+      for (int sub = 0; sub < 4; ++sub)
+        for (int m = 0; m < M; ++m)
+          for (int n = 0; n < nhalf; ++n) {
+            float acc = D[((size_t)sub * M + m) * nhalf + n];
+            for (int kk = 0; kk < 16; ++kk) {
+              const float ah = emu_half_at(a_stage.data(), fe_gemm_a_tile_offset(sub, 0) + fe_gemm_operand_offset(M, m, kk));
+              const float al = emu_half_at(a_stage.data(), fe_gemm_a_tile_offset(sub, 1) + fe_gemm_operand_offset(M, m, kk));
+              const float bh = emu_half_at(b_stage, fe_gemm_b_tile_offset(nhalf, sub, 0) + fe_gemm_operand_offset(nhalf, n, kk));
+              const float bl = emu_half_at(b_stage, fe_gemm_b_tile_offset(nhalf, sub, 1) + fe_gemm_operand_offset(nhalf, n, kk));
+              acc += ah * bh + al * bh + ah * bl;
+            }
+            D[((size_t)sub * M + m) * nhalf + n] = acc;
+          }
+    }
+    // drain: thread (frame m, column group cg); two emission buffers indexed by group parity
+    const int cpg = nhalf / FE_DRAIN_GROUPS;
+    for (int m = 0; m < M; ++m) {
+      const float us2 = unscale[m] * unscale[m];
+      for (int cg = 0; cg < FE_DRAIN_GROUPS; ++cg) {
+        fe_drain_state st;
+        fe_drain_init(st, dids[cg * cpg / 2]);
+        float* e_col = E.data() + (size_t)(cg & (nbuf - 1)) * (nfil + 1) * M + m;
+        for (int k0 = cg * cpg; k0 < (cg + 1) * cpg; k0 += 8) {
+          float ce[8], co[8], se[8], so[8];
+          for (int i = 0; i < 8; ++i) {
+            ce[i] = D[((size_t)0 * M + m) * nhalf + k0 + i];
+            co[i] = D[((size_t)1 * M + m) * nhalf + k0 + i];
+            se[i] = D[((size_t)2 * M + m) * nhalf + k0 + i];
+            so[i] = D[((size_t)3 * M + m) * nhalf + k0 + i];
+          }
+          fe_drain_pairs<4>(dw + k0 / 2, dids + k0 / 2, dctl[k0 >> 3], ce, co, se, so, st, e_col, us2);
+        }
+        if (cg == FE_DRAIN_GROUPS - 1) {
+          const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
+          const float re = mre[m] * bs, im = mim[m] * bs;
+          fe_drain_mid(dw + nhalf / 2, dids + nhalf / 2, dctl[nhalf >> 3], fmaf(re, re, im * im), st, e_col, us2);
+        }
+        fe_drain_flush(st, e_col, us2);
       }
     }
     // finalize
@@ -249,8 +246,8 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
       const int gi = g.g0 + m, row = gi / nF, t = gi - row * nF;
       for (int f = 0; f < nfil; ++f) {
         const size_t bs = (size_t)(nfil + 1) * M;
-        float v = 0.0f;
-        for (int cg = 0; cg < FE_DRAIN_GROUPS; ++cg) v += E[cg * bs + (size_t)f * M + m];
+        float v = E[(size_t)f * M + m] + E[bs + (size_t)f * M + m];
+        if (nbuf == 4) v += E[2 * bs + (size_t)f * M + m] + E[3 * bs + (size_t)f * M + m];
         energies[((size_t)row * nfil + f) * nF + t] = v;
       }
     }
