@@ -17,7 +17,7 @@ struct alignas(8) fe_c2 {
   float x, y;
 };
 
-#define FE_BLOB_MAGIC 0xB200FE02u
+#define FE_BLOB_MAGIC 0xB200FE03u
 
 // Header of the constant-table blob produced by b200fe_tables_pack (all offsets in bytes from the
 // start of the blob, 16-byte aligned).  The blob is position independent: the same bytes are valid
@@ -44,11 +44,11 @@ struct fe_blob_header {
   int32_t off_gemm_b;      // __half operand tiles, see fe_gemm_layout.h
   int32_t gemm_b_bytes;
   int32_t off_gemm_mid;    // float[2][gemm_kpairs]  true-unit weights of bin n_fft/4 (Re from a_e, Im from a_o)
-  // sliding even/odd filter accumulators of the drain (fe_gemm_layout.h)
-  int32_t off_gemm_dw;     // fe_drain_w[gemm_nhalf/2 + 1]   per column pair (+ bin n_fft/4): weights of the 4 classes x 2 halves
-  int32_t off_gemm_dctl;   // uint32[gemm_nhalf/8 + 1]       per 4-pair batch: switch flags, bit 8*(pair % 4) + 2*a + h
-  int32_t off_gemm_dids;   // fe_drain_ids[gemm_nhalf/2 + 1] filter rows of the 8 halves after the pair's switches
-  int32_t gemm_nbuf;       // emission buffers of the drain: 2 (indexed by column-group parity) or 4 (one per group)
+  // sliding even/odd filter accumulators of the drain (fe_gemm_layout.h); PP = fe_drain_pairs_padded(gemm_nhalf)
+  int32_t off_gemm_dw;     // fe_drain_w[2 runs][PP]   per column pair (+ the virtual pair of column n_fft/4): weights
+  int32_t off_gemm_dctl;   // uint32[2 runs][PP]       per pair: switch codes and new targets
+  int32_t off_gemm_dids;   // fe_drain_hdr             first / last targets of the runs, straddler merge flags
+  int32_t gemm_nbuf;       // (unused since the drain stores final energies directly; kept for layout stability)
   int32_t reserved[6];
 };
 

@@ -178,84 +178,63 @@ FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scal
   }
 }
 
-// ---- drain: sliding even/odd filter accumulators over column pairs (tables: fe_gemm_layout.h) ---------------------
+// ---- drain: sliding even/odd filter accumulators over column pairs (tables and protocol: fe_gemm_layout.h) ---------
 struct fe_drain_state {
-  fe_f2 acc[4];   // class a: .x even columns, .y odd columns
-  int off[8];     // half 2a + h: BYTE offset of its filter's row in the emission scratch (dummy row: none)
+  fe_f2 acc[2];    // class = filter parity: .x even columns, .y odd columns
+  float pend[2];   // odd-column part of a segment whose even half has not switched yet
+  int tgt[2];      // filter the class is aimed at (FE_DRAIN_NONE: none)
 };
 
-// the walk of a column group starts with the halves already aimed at the filters of the group's first pair
-FE_HD void fe_drain_init(fe_drain_state& st, const fe_drain_ids& first) {
+FE_HD void fe_drain_init(fe_drain_state& st, const fe_drain_hdr& hdr, int run) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) st.acc[a] = fe_f2{0.0f, 0.0f};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) st.off[i] = first.off[i];
+  for (int c = 0; c < 2; ++c) {
+    st.acc[c] = fe_f2{0.0f, 0.0f};
+    st.pend[c] = 0.0f;
+    st.tgt[c] = hdr.first[run][c];
+  }
 }
 
-// adds one finished half accumulator to the frame's filter sum (e_col = this frame's column of the [filter + 1][128]
-// array; halves without a filter point at the dummy last row, so there is nothing to test)
-FE_HD void fe_drain_emit(float* e_col, int off, float v, float us2) {
-  float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(e_col) + off);
-  *p = fmaf(v, us2, *p);
-}
-
-// the (thread-uniform) switches of one pair: bit 2a + h; classes without a switch are skipped by a uniform branch
-FE_HD void fe_drain_switch(unsigned flags, const fe_drain_ids& ids, fe_drain_state& st, float* e_col, float us2) {
+// the (thread-uniform) switches of one pair; `emit(filter, value)` receives a finished segment (scaled units)
+template <class Emit>
+FE_HD void fe_drain_switch(unsigned ctl, fe_drain_state& st, Emit& emit) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    if (flags & (3u << (2 * a))) {
-      if (flags & (1u << (2 * a))) {
-        fe_drain_emit(e_col, st.off[2 * a], st.acc[a].x, us2);
-        st.acc[a].x = 0.0f;
-        st.off[2 * a] = ids.off[2 * a];
-      }
-      if (flags & (2u << (2 * a))) {
-        fe_drain_emit(e_col, st.off[2 * a + 1], st.acc[a].y, us2);
-        st.acc[a].y = 0.0f;
-        st.off[2 * a + 1] = ids.off[2 * a + 1];
-      }
+  for (int c = 0; c < 2; ++c) {
+    if (ctl & (1u << (2 * c))) {
+      st.pend[c] = st.acc[c].y;
+      st.acc[c].y = 0.0f;
+    }
+    if (ctl & (2u << (2 * c))) {
+      emit(st.tgt[c], st.acc[c].x + st.pend[c]);
+      st.acc[c].x = 0.0f;
+      st.pend[c] = 0.0f;
+      st.tgt[c] = (int)((ctl >> (8 + 8 * c)) & 255u);
     }
   }
 }
 
-// NP consecutive column pairs starting at a multiple of 4 pairs (ctl = the batch's switch word, w / ids at the first
-// pair): |X[k]|^2 = (ce+co)^2 + (se+so)^2 and |X[n_fft/2 - k]|^2 = (ce-co)^2 + (so-se)^2 for two columns at a time.
-template <int NP>
-FE_HD void fe_drain_pairs(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, const float* ce, const float* co,
-                          const float* se, const float* so, fe_drain_state& st, float* e_col, float us2) {
+// One column pair of run RUN: |X[k]|^2 = (ce+co)^2 + (se+so)^2 (run 0) or |X[n_fft/2 - k]|^2 = (ce-co)^2 + (so-se)^2
+// (run 1) for the two columns at a time, then the two classes' weighted sums.
+template <int RUN, class Emit>
+FE_HD void fe_drain_pair(fe_f2 c0, fe_f2 c1, fe_f2 s0, fe_f2 s1, const fe_drain_w& w, unsigned ctl, fe_drain_state& st,
+                         Emit& emit) {
   const fe_f2 neg = fe_f2{-1.0f, -1.0f};
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    const fe_f2 c0 = fe_f2{ce[2 * p], ce[2 * p + 1]}, c1 = fe_f2{co[2 * p], co[2 * p + 1]};
-    const fe_f2 s0 = fe_f2{se[2 * p], se[2 * p + 1]}, s1 = fe_f2{so[2 * p], so[2 * p + 1]};
-    const fe_f2 re1 = fe_add2(c0, c1), im1 = fe_add2(s0, s1), re2 = fe_fma2(c1, neg, c0), im2 = fe_fma2(s0, neg, s1);
-    const fe_f2 p1 = fe_fma2(re1, re1, fe_mul2(im1, im1));   // |X[k]|^2 (scaled units)
-    const fe_f2 p2 = fe_fma2(re2, re2, fe_mul2(im2, im2));   // |X[n_fft/2 - k]|^2
-    const unsigned fl = (ctl >> (8 * p)) & 255u;
-    if (fl) fe_drain_switch(fl, ids[p], st, e_col, us2);
-    const fe_drain_w t = w[p];
-    st.acc[0] = fe_fma2(p1, fe_f2{t.w[0][0], t.w[0][1]}, st.acc[0]);
-    st.acc[1] = fe_fma2(p1, fe_f2{t.w[1][0], t.w[1][1]}, st.acc[1]);
-    st.acc[2] = fe_fma2(p2, fe_f2{t.w[2][0], t.w[2][1]}, st.acc[2]);
-    st.acc[3] = fe_fma2(p2, fe_f2{t.w[3][0], t.w[3][1]}, st.acc[3]);
-  }
+  const fe_f2 re = RUN == 0 ? fe_add2(c0, c1) : fe_fma2(c1, neg, c0);
+  const fe_f2 im = RUN == 0 ? fe_add2(s0, s1) : fe_fma2(s0, neg, s1);
+  const fe_f2 pw = fe_fma2(re, re, fe_mul2(im, im));
+  if (ctl & 15u) fe_drain_switch(ctl, st, emit);
+  st.acc[0] = fe_fma2(pw, fe_f2{w.w[0][0], w.w[0][1]}, st.acc[0]);
+  st.acc[1] = fe_fma2(pw, fe_f2{w.w[1][0], w.w[1][1]}, st.acc[1]);
 }
 
-// bin n_fft/4 (pair index nhalf/2 of the tables, even half only): only the ascending run's classes
-FE_HD void fe_drain_mid(const fe_drain_w* w, const fe_drain_ids* ids, unsigned ctl, float p_mid, fe_drain_state& st,
-                        float* e_col, float us2) {
-  const unsigned fl = ctl & 0x05u;   // halves (class 0, even) and (class 1, even)
-  if (fl) fe_drain_switch(fl, ids[0], st, e_col, us2);
-  st.acc[0].x = fmaf(p_mid, w[0].w[0][0], st.acc[0].x);
-  st.acc[1].x = fmaf(p_mid, w[0].w[1][0], st.acc[1].x);
+// the virtual pair of column n_fft/4: run 0 adds the producers' bin (power p_mid, even half), run 1 only switches
+template <class Emit>
+FE_HD void fe_drain_last_pair(float p_mid, const fe_drain_w& w, unsigned ctl, fe_drain_state& st, Emit& emit) {
+  if (ctl & 15u) fe_drain_switch(ctl, st, emit);
+  st.acc[0].x = fmaf(p_mid, w.w[0][0], st.acc[0].x);
+  st.acc[1].x = fmaf(p_mid, w.w[1][0], st.acc[1].x);
 }
 
-FE_HD void fe_drain_flush(fe_drain_state& st, float* e_col, float us2) {
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    fe_drain_emit(e_col, st.off[2 * a], st.acc[a].x, us2);
-    fe_drain_emit(e_col, st.off[2 * a + 1], st.acc[a].y, us2);
-  }
-}
+// what a run still holds for class c after its last pair (the last segment's sum)
+FE_HD float fe_drain_leftover(const fe_drain_state& st, int c) { return (st.acc[c].x + st.acc[c].y) + st.pend[c]; }
 
 #endif  // FE_GEMM_CUH_

@@ -23,23 +23,36 @@
 #define FE_GEMM_STAGE_J 32        // sample pairs per pipeline stage: one K=16 MMA step per sub-GEMM
 
 // ---- drain tables ----------------------------------------------------------------------------------------
-// A drain thread owns one frame (TMEM lane) and one of FE_DRAIN_GROUPS column groups (nhalf / 4 consecutive GEMM
-// columns).  Column k carries bin k (the ascending "lo" run) and bin n_fft/2 - k (the descending "hi" run).  Every
-// bin may have at most one even-indexed and one odd-indexed filter with non-zero weight (true for triangular
-// banks), so each run needs two accumulators: class a = 2*run + parity.  Columns are processed in PAIRS (2p, 2p+1)
-// with packed fp32x2 arithmetic (one issue slot for two columns), so every class has two independent halves h (even /
-// odd column), each with its own target filter: half (a, h) is emitted (added to the frame's filter sum) and
-// re-targeted before pair p whenever the filter of class a at column 2p + h differs from the one at column 2p + h - 2
-// ("switch").  Switches are the same for all threads: table driven and branch-uniform.
+// A drain thread owns one frame (TMEM lane) and one RUN of bins: GEMM column k carries bin k (run 0, ascending) and
+// bin n_fft/2 - k (run 1, descending); run 0 also takes bin n_fft/4 (evaluated by the producers) as column n_fft/4.
+// Both runs walk ALL columns 0 .. n_fft/4 - 1 in PAIRS (2p, 2p+1) with packed fp32x2 arithmetic (one issue slot for
+// two columns), then one more (virtual) pair for column n_fft/4.  Every bin may carry at most one even-indexed and
+// one odd-indexed filter (true for triangular banks), so a run needs two accumulators (class = filter parity), each
+// with an even-column half (.x) and an odd-column half (.y).  Along a run the filter of a class is piecewise
+// constant; a SEGMENT is a maximal range of columns with the same filter (or none).  The host packer normalises the
+// segments (short filter-less ranges are absorbed with zero weights) and requires every segment to span >= 3
+// columns; a filter then occupies exactly one segment of one class of a run (or the last segment of both runs when
+// it straddles bin n_fft/4), so the value a thread holds when a segment ends is the filter's FINAL energy for the
+// frame: it is stored straight to the workspace (no shared-memory scratch, no second pass).
+//   O switch at pair p: column 2p+1 is the first odd column of a new segment   -> pend = acc.y, acc.y = 0
+//   E switch at pair p: column 2p   is the first even column of a new segment  -> store acc.x + pend, acc.x = pend = 0,
+//                       the class is re-targeted at the new segment's filter
+// (O comes in the same pair as E or in the pair before it; switches are the same for all threads: table driven,
+// branch-uniform.)  After the last pair the two runs' leftovers are the straddling filters: run 1 hands its pair to
+// run 0 through shared memory where the targets coincide.
 struct alignas(16) fe_drain_w {
-  float w[4][2];     // per class a: weights at columns (2p, 2p+1); classes 0,1: bin k (even, odd filter); 2,3: bin n_fft/2 - k
+  float w[2][2];     // [class = filter parity][half]: weights at columns (2p, 2p+1)
 };
-struct alignas(16) fe_drain_ids {
-  int16_t off[8];    // per half 2a + h, once this pair's switches are done: BYTE offset (filter * 128 * 4) of its filter's
-                     // row in the frame-major emission scratch; n_filter * 512 (a dummy row) while it has none.  The first
-                     // pair of a column group carries no switch flags: the walk starts from that pair's entry.
+// control word of a pair: bits 0-1 class 0 (bit 0: O switch, bit 1: E switch), bits 2-3 class 1,
+// bits 8-15 / 16-23: filter the class is aimed at after its E switch (FE_DRAIN_NONE: no filter)
+#define FE_DRAIN_NONE 255
+struct fe_drain_hdr {
+  int32_t first[2][2];   // [run][class] filter of the first segment (FE_DRAIN_NONE: none)
+  int32_t last[2][2];    // [run][class] filter of the last segment
+  int32_t merge[2];      // [class] 1: the last segments of the two runs are the same filter (run 0 stores the sum)
+  int32_t pad[2];
 };
-#define FE_DRAIN_GROUPS 4   // column groups (warps per TMEM lane quarter)
+FE_HD int fe_drain_pairs_padded(int nhalf) { return ((nhalf / 2 + 1) + 3) & ~3; }   // pairs per run incl. the virtual one, x4
 
 // UMMA K-major, no-swizzle operand tile of `rows` rows x 16 K-values (one K=16 MMA step):
 // [K chunk of 8][row][8 halfs] -> descriptor LBO (K-chunk stride) = rows*16 B, SBO (8-row group) = 128 B.

@@ -26,7 +26,7 @@ gemm_geom geometry(const b200fe_params* p) {
   const int kpairs = p->win_length / 2;
   const int nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return g;
-  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM
+  if (nhalf % 8 != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM
   g.ok = true;
   g.kpairs = kpairs;
   g.nhalf = nhalf;
@@ -48,29 +48,30 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
   off = fe_align16(off + h->gemm_b_bytes);
   h->off_gemm_mid = (int32_t)off;
   off = fe_align16(off + (int64_t)2 * g.kpairs * 4);
+  const int pp = fe_drain_pairs_padded(g.nhalf);
   h->off_gemm_dw = (int32_t)off;
-  off = fe_align16(off + (int64_t)(g.nhalf / 2 + 1) * sizeof(fe_drain_w));
+  off = fe_align16(off + (int64_t)2 * pp * sizeof(fe_drain_w));
   h->off_gemm_dctl = (int32_t)off;
-  off = fe_align16(off + (int64_t)(g.nhalf / 8 + 1) * 4);
+  off = fe_align16(off + (int64_t)2 * pp * 4);
   h->off_gemm_dids = (int32_t)off;
-  off = fe_align16(off + (int64_t)(g.nhalf / 2 + 1) * sizeof(fe_drain_ids));
+  off = fe_align16(off + (int64_t)sizeof(fe_drain_hdr));
   h->gemm_ok = 1;  // provisional: fe_gemm_pack clears it when the window / filterbank do not qualify
   return off;
 }
 
-// Drain tables (fe_gemm_layout.h): per column pair the weights of the four accumulator classes x two halves, the
-// switch flags and the filter rows after the switches.  Returns false when the filterbank does not qualify (a bin
-// with two filters of the same parity, or emission buffers that do not fit the A slots they alias).
+// Drain tables (fe_gemm_layout.h): per run and column pair the weights of the two filter-parity classes x two halves,
+// the switch codes and the filters the classes are aimed at.  Returns false when the filterbank does not qualify: a
+// bin with two filters of the same parity, a filter whose support along a run is not one range of >= 3 columns, or
+// a filter without any bin (its energy would never be stored).
 static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, int nhalf, char* base) {
-  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nfil > FE_GEMM_MAX_FILTERS) return false;
+  if (nhalf % 8 != 0 || nfil > FE_GEMM_MAX_FILTERS || nfil >= FE_DRAIN_NONE) return false;
+  const int pp = fe_drain_pairs_padded(nhalf), npairs = nhalf / 2, nyq = 2 * nhalf;
   fe_drain_w* dw = (fe_drain_w*)(base + h->off_gemm_dw);
   uint32_t* dctl = (uint32_t*)(base + h->off_gemm_dctl);
-  fe_drain_ids* dids = (fe_drain_ids*)(base + h->off_gemm_dids);
-  const int npairs = nhalf / 2;
-  memset(dw, 0, (size_t)(npairs + 1) * sizeof(fe_drain_w));
-  memset(dctl, 0, (size_t)(nhalf / 8 + 1) * 4);
-  const int nyq = 2 * nhalf, ppg = npairs / FE_DRAIN_GROUPS;   // pairs per column group
-  std::vector<unsigned> touched(nfil, 0u);
+  fe_drain_hdr* hdr = (fe_drain_hdr*)(base + h->off_gemm_dids);
+  memset(dw, 0, (size_t)2 * pp * sizeof(fe_drain_w));
+  memset(dctl, 0, (size_t)2 * pp * 4);
+  memset(hdr, 0, sizeof(*hdr));
   // filter of parity `par` with weight on `bin` (-1: none, -2: more than one)
   auto filter_of = [&](int bin, int par) {
     int f_found = -1;
@@ -78,50 +79,67 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
       if (fbank[(int64_t)bin * nfil + f] != 0.0f) { if (f_found >= 0) return -2; f_found = f; }
     return f_found;
   };
-  for (int g = 0; g < FE_DRAIN_GROUPS; ++g) {
-    int cur[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
-    // the last group also takes bin n_fft/4 as the even column of one more (half) pair
-    const int p_end = (g + 1) * ppg + (g == FE_DRAIN_GROUPS - 1 ? 1 : 0);
-    for (int p = g * ppg; p < p_end; ++p) {
-      unsigned flags = 0;
-      for (int hh = 0; hh < 2; ++hh) {
-        const int k = 2 * p + hh;
-        if (k > nhalf) continue;                     // the odd half of the bin-n_fft/4 entry does not exist
-        for (int run = 0; run < 2; ++run) {
-          if (k == nhalf && run == 1) continue;      // bin n_fft/4 belongs to the ascending run only
-          const int bin = run == 0 ? k : nyq - k;
-          for (int par = 0; par < 2; ++par) {
-            const int a = 2 * run + par;
-            const int f = filter_of(bin, par);
-            if (f == -2) return false;
-            if (f < 0) continue;
-            dw[p].w[a][hh] = fbank[(int64_t)bin * nfil + f];
-            touched[f] |= 1u << g;
-            if (f != cur[a][hh]) {
-              if (p != g * ppg) flags |= 1u << (2 * a + hh);   // the group's first pair: the walk starts aimed at it
-              cur[a][hh] = f;
-            }
-          }
-        }
+  std::vector<int> seen(nfil, 0);
+  const int ncol = nhalf + 2;   // columns 0 .. nhalf-1, column nhalf (bin n_fft/4: run 0 only) and one virtual odd column
+  for (int run = 0; run < 2; ++run) {
+    for (int par = 0; par < 2; ++par) {
+      std::vector<int> f(ncol, -1);
+      const int nreal = run == 0 ? nhalf + 1 : nhalf;
+      for (int k = 0; k < nreal; ++k) {
+        f[k] = filter_of(run == 0 ? k : nyq - k, par);
+        if (f[k] == -2) return false;
       }
-      for (int a = 0; a < 4; ++a)
-        for (int hh = 0; hh < 2; ++hh)
-          dids[p].off[2 * a + hh] = (int16_t)((cur[a][hh] < 0 ? nfil : cur[a][hh]) * FE_GEMM_TILE_M * 4);
-      dctl[p / 4] |= flags << (8 * (p % 4));
+      // filter-less ranges shorter than 3 columns are absorbed by the following (else the preceding) segment
+      for (int k = 0; k < nreal;) {
+        int e = k;
+        while (e + 1 < nreal && f[e + 1] == f[k]) ++e;
+        if (f[k] == -1 && e - k + 1 < 3) {
+          const int repl = e + 1 < nreal ? f[e + 1] : (k > 0 ? f[k - 1] : -1);
+          for (int i = k; i <= e; ++i) f[i] = repl;
+        }
+        k = e + 1;
+      }
+      for (int k = nreal; k < ncol; ++k) f[k] = f[nreal - 1];   // virtual columns continue the last segment
+      // every segment >= 3 columns (the last one may be shorter only through its virtual columns), a filter in
+      // at most one segment of the class
+      std::vector<int> seg_of(nfil, 0);
+      for (int k = 0; k < ncol;) {
+        int e = k;
+        while (e + 1 < ncol && f[e + 1] == f[k]) ++e;
+        if (e - k + 1 < 3) return false;
+        if (f[k] >= 0) {
+          if (seg_of[f[k]]++) return false;
+          seen[f[k]] |= 1 << run;
+        }
+        k = e + 1;
+      }
+      hdr->first[run][par] = f[0] < 0 ? FE_DRAIN_NONE : f[0];
+      hdr->last[run][par] = f[ncol - 1] < 0 ? FE_DRAIN_NONE : f[ncol - 1];
+      for (int p = 0; p <= npairs; ++p) {
+        fe_drain_w& w = dw[run * pp + p];
+        for (int hh = 0; hh < 2; ++hh) {
+          const int k = 2 * p + hh;
+          if (k < nreal && f[k] >= 0) w.w[par][hh] = fbank[(int64_t)(run == 0 ? k : nyq - k) * nfil + f[k]];
+        }
+        uint32_t code = 0;
+        if (p > 0 && f[2 * p + 1] != f[2 * p - 1]) code |= 1u;   // O switch
+        if (p > 0 && f[2 * p] != f[2 * p - 2]) code |= 2u;       // E switch
+        const uint32_t tgt = f[2 * p] < 0 ? FE_DRAIN_NONE : (uint32_t)f[2 * p];
+        dctl[run * pp + p] |= (code << (2 * par)) | (tgt << (8 + 8 * par));
+      }
     }
   }
-  // Column groups that share a filter must emit into different buffers.  Two buffers indexed by group parity do
-  // when a filter is only ever shared by adjacent groups; otherwise every group gets its own buffer (if the
-  // n_filter x 128 arrays still fit the 64 KB of A slots they alias).
-  bool adjacent_only = true;
-  for (int f = 0; f < nfil; ++f) {
-    const unsigned m = touched[f];
-    if (m == 0) continue;
-    const unsigned low = m & (0u - m);
-    if (m != low && m != (low | (low << 1))) adjacent_only = false;
+  for (int par = 0; par < 2; ++par) {
+    const int a = hdr->last[0][par], b = hdr->last[1][par];
+    hdr->merge[par] = (a == b && a != FE_DRAIN_NONE) ? 1 : 0;
   }
-  h->gemm_nbuf = adjacent_only ? 2 : FE_DRAIN_GROUPS;
-  return h->gemm_nbuf * (nfil + 1) * FE_GEMM_TILE_M * 4 <= 2 * 8 * fe_gemm_tile_bytes(FE_GEMM_TILE_M);   // both A slots (+1: the dummy row)
+  // a filter reached by both runs must be the straddler of its class; a filter reached by none is never stored
+  for (int f = 0; f < nfil; ++f) {
+    if (seen[f] == 0) return false;
+    if (seen[f] == 3 && !(hdr->merge[f & 1] && hdr->last[0][f & 1] == f)) return false;
+  }
+  h->gemm_nbuf = 0;
+  return true;
 }
 
 int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* window, const float* fbank,

@@ -4,25 +4,25 @@
 // frames = the 128 TMEM lanes of one M=128 MMA, whatever utterances they belong to, so every tile is full.
 // One persistent CTA per SM walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...
 //
-//   loader warp   per tile: the hop blocks the tile's frames need, once each, as a handful of TMA tensor boxes
-//                 {32 floats, hop/32, 2^k hop blocks} with the 128-byte swizzle: hop blocks sit densely in shared
-//                 memory and lane <-> frame reads are still conflict-free (consecutive blocks land on different
-//                 swizzle phases because hop/32 is odd or the phase advances by hop/32 mod 8).  A small 1-D bulk
-//                 copy costs the TMA unit ~90 cycles whatever its size (130 per tile took 12 k cycles), hence
-//                 boxes.  Reflect-padded edge blocks are synthesised with plain loads.  Per stage: the 32 KB of
-//                 DFT operand tiles.
-//   MMA warp      one thread: 12 tcgen05.mma (M=128, N=n_fft/4, K=16; 4 sub-GEMMs x 3 split-fp16 products) per
-//                 stage into the 4 TMEM accumulators, tcgen05.commit -> mbarriers
-//   16 worker warps, all doing the same thing in phases:
-//     scout       max|x| per hop block (shared memory) -> per-frame power-of-two scale
-//     produce     fold + scale + fp16 hi/lo split of 16 sample pairs per thread into the UMMA A tiles; the two
-//                 halves of the warps (0-7 / 8-15) take alternate stages, i.e. alternate A slots
-//     drain       tcgen05.ld of the four accumulators, powers, sliding even/odd triangular-filter sums
-//                 (fe_gemm_layout.h), all 16 warps: warp = (TMEM lane quarter, column group)
-//     finalize    energies of the tile -> workspace [row][filter][frame] (+ per-group maximum for top_db)
-// TMEM holds exactly the four accumulators (4 x 128 columns), so the MMAs of a tile and its drain cannot
-// overlap; everything else does: production runs one stage ahead of the MMAs, the next tile's samples and
-// operand stages are loaded during MMA tail and drain.
+// Warp roles (23 warps):
+//    0- 7  drain      warp = (TMEM lane quarter, run): tcgen05.ld of the four accumulators, packed fp32x2 powers of the
+//                     run's bins (run 0: bin k, run 1: bin n_fft/2 - k) and sliding even/odd triangular-filter sums
+//                     over column pairs (fe_gemm_layout.h).  A finished filter segment is the filter's final energy for
+//                     the frame and goes straight to the workspace [row][filter][frame]; the two runs meet once per
+//                     tile for the filters that straddle bin n_fft/4.  TMEM is released after the last tcgen05.ld.
+//    8-19  producers  three groups of four warps (lane = frame).  Per tile: max|x| per hop block -> per-frame
+//                     power-of-two scale, then production units u = 2*stage + K half (16 sample pairs of every frame:
+//                     fold + scale + fp16 hi/lo split into the UMMA A tiles), unit u by group u % 3.  The A slots are
+//                     not aliased by anything, so the first two stages of tile i+1 are produced while tile i is drained.
+//   20-21  MMA        one issuing thread per sub-GEMM pair (ce, co / se, so): per stage 3 x 2 tcgen05.mma (M=128,
+//                     N=n_fft/4, K=16: hi*hi + lo*hi + hi*lo) into the 4 TMEM accumulators, tcgen05.commit -> mbarriers
+//   22     loader     per tile: the hop blocks the tile's frames need, once each, as a handful of TMA tensor boxes
+//                     {32 floats, hop/32, 2^k hop blocks} with the 128-byte swizzle: hop blocks sit densely in shared
+//                     memory and lane <-> frame reads are still conflict-free.  A small 1-D bulk copy costs the TMA
+//                     unit ~90 cycles whatever its size, hence boxes.  Reflect-padded edge blocks are synthesised
+//                     with plain loads.  Per stage: the 32 KB of DFT operand tiles.
+// TMEM holds exactly the four accumulators (4 x 128 columns), so the MMAs of a tile and its drain cannot overlap;
+// the tile period is MMA phase + drain, everything else (sample loads, scout, production, stores) runs beside them.
 #include <atomic>
 
 #include "fe_tc.cuh"
@@ -33,12 +33,15 @@
 
 namespace {
 
-constexpr int kWorkerWarps = 16;
-constexpr int kWorkerThreads = kWorkerWarps * 32;
-constexpr int kMmaWarp0 = 16;   // warps 16, 17: MMA issuers, two sub-GEMMs each (ce, co / se, so)
+constexpr int kDrainWarps = 8;        // warps 0..7: quarter = warp & 3, run = warp >> 2
+constexpr int kProducerWarp0 = 8;
+constexpr int kProducerGroups = 3;    // (tests/emu/fe_emu.cpp mirrors the unit -> group mapping)
+constexpr int kProducerWarps = 4 * kProducerGroups;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kMmaWarp0 = kProducerWarp0 + kProducerWarps;   // warps 20, 21: MMA issuers, two sub-GEMMs each (ce, co / se, so)
 constexpr int kNumMmaWarps = 2;
-constexpr int kLoaderWarp = 18;
-constexpr int kThreads = 19 * 32;  // (registers are allocated per 4 warps: 20 warps' worth -> 96 registers per thread)
+constexpr int kLoaderWarp = kMmaWarp0 + kNumMmaWarps;
+constexpr int kThreads = (kLoaderWarp + 1) * 32;
 constexpr int kTileM = FE_GEMM_TILE_M;
 constexpr int kMaxSlots = 132;                    // hop blocks of a tile: 128 + 1 + one more per utterance boundary
 constexpr int kAStageBytes = 8 * 2 * kTileM * 16; // 32 KB: [sub 4][hi, lo] tiles of 128 rows x 16 K
@@ -56,23 +59,25 @@ struct stream_args {
 };
 
 struct smem_layout {
-  int samp, a_stage, b_stage, dw, dids, dctl, mid, gmax, us2, midp, bars, tmem_slot, total;
+  int samp, a_stage, b_stage, dw, dctl, dhdr, mid, gmax, us2, midp, exch, bars, tmem_slot, total;
 };
 
 __host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpairs) {
   smem_layout L;
+  const int pp = fe_drain_pairs_padded(nhalf);
   int off = 0;
   L.samp = off;      off += kMaxSlots * hop * 4;            // dense hop-block rows, 128-byte swizzled (base 1024-aligned)
   off = (off + 127) & ~127;
   L.a_stage = off;   off += 2 * kAStageBytes;
   L.b_stage = off;   off += 2 * fe_gemm_b_stage_bytes(nhalf);
-  L.dw = off;        off += (nhalf / 2 + 1) * (int)sizeof(fe_drain_w);
-  L.dids = off;      off += (nhalf / 2 + 1) * (int)sizeof(fe_drain_ids);
-  L.dctl = off;      off += ((nhalf / 8 + 1) * 4 + 15) & ~15;
+  L.dw = off;        off += 2 * pp * (int)sizeof(fe_drain_w);
+  L.dctl = off;      off += 2 * pp * 4;
+  L.dhdr = off;      off += (int)sizeof(fe_drain_hdr);
   L.mid = off;       off += kpairs * 4;          // interleaved weights of bin n_fft/4: even j -> Re, odd j -> Im
   L.gmax = off;      off += ((kMaxSlots + 1) * 4 + 15) & ~15;   // max |x| per hop block of the tile
-  L.us2 = off;       off += kTileM * 4;
-  L.midp = off;      off += 4 * kTileM * 8;   // [producer half-group 2][K half 2][frame] (Re, Im) partials of bin n_fft/4
+  L.us2 = off;       off += 2 * kTileM * 4;                       // [tile parity][frame] unscale^2
+  L.midp = off;      off += 2 * kProducerGroups * kTileM * 8;     // [tile parity][producer group][frame] (Re, Im) partials of bin n_fft/4
+  L.exch = off;      off += 2 * 2 * kTileM * 4;                   // [tile parity][class][frame] run 1 -> run 0 straddler partials
   L.bars = off;      off += 16 * 8;
   L.tmem_slot = off; off += 16;
   L.total = off;
@@ -80,7 +85,7 @@ __host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpair
 }
 
 enum { BAR_SAMP_FULL = 0, BAR_SAMP_EMPTY = 1, BAR_A_FULL = 2, BAR_B_FULL = 4, BAR_STAGE_FREE = 6, BAR_ACC_FULL = 8,
-       BAR_ACC_EMPTY = 9, BAR_SCOUT_FULL = 10, BAR_ZERO_DONE = 11, BAR_COUNT = 12 };
+       BAR_ACC_EMPTY = 9, BAR_PROD_DONE = 10, BAR_COUNT = 12 };
 
 #ifdef FE_GEMM_TRACE
 #define ST_TRACE(ev, it, q) do { if (blockIdx.x == 0 && (it) < 8) { ((long long*)(a.error_flag + 64))[((it) * 8 + (q)) * 16 + (ev)] = clock64(); } } while (0)
@@ -127,7 +132,24 @@ __device__ __forceinline__ void scout_rows(const unsigned char* s_samp, float* s
   }
 }
 
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory"); }
+__device__ __forceinline__ void quarter_bar(int quarter) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory"); }
+
+// a finished filter segment of the drain: final energy of (frame, filter) -> workspace
+struct emit_store {
+  float* dst;        // energies + (row * n_filter) * n_frames + t
+  size_t n_frames;
+  int n_filter;
+  bool valid;
+  float us2, vmax;
+  __device__ __forceinline__ void operator()(int f, float v) {
+    if (valid && f < n_filter) {
+      const float e = v * us2;
+      dst[(size_t)f * n_frames] = e;
+      vmax = fmaxf(vmax, e);
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_constant__ tmaps8 maps, const stream_args a) {
@@ -137,8 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
   const int nF = a.n_frames, hop = a.hop, nfil = a.n_filter;
-  const int nbuf = h->gemm_nbuf;   // emission buffers of the drain (2 or 4)
   const int rs = hop * 4;        // bytes per hop-block row (dense; the 128-byte swizzle keeps lane <-> frame reads conflict-free)
+  const int pp = fe_drain_pairs_padded(a.nhalf);
 
   if (!h->gemm_ok) {
     // tables without the variant's tiles (a C-ABI caller that set variant = DFT_GEMM without asking
@@ -149,13 +171,13 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   }
   unsigned char* s_samp = smem + L.samp;
   fe_drain_w* s_dw = reinterpret_cast<fe_drain_w*>(smem + L.dw);
-  fe_drain_ids* s_dids = reinterpret_cast<fe_drain_ids*>(smem + L.dids);
   uint32_t* s_dctl = reinterpret_cast<uint32_t*>(smem + L.dctl);
+  fe_drain_hdr* s_dhdr = reinterpret_cast<fe_drain_hdr*>(smem + L.dhdr);
   float* s_mid = reinterpret_cast<float*>(smem + L.mid);
   float* s_gmax = reinterpret_cast<float*>(smem + L.gmax);
   float* s_us2 = reinterpret_cast<float*>(smem + L.us2);
   float2* s_midp = reinterpret_cast<float2*>(smem + L.midp);
-  float* s_E = reinterpret_cast<float*>(smem + L.a_stage);   // drain scratch [nbuf][n_filter + 1][128] aliases the A slots (from slot 0 on)
+  float* s_exch = reinterpret_cast<float*>(smem + L.exch);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const uint32_t bars = smem_u32(smem + L.bars);
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
@@ -163,11 +185,11 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   // ---- one-time setup -----------------------------------------------------------------------------
   {
     const fe_drain_w* gdw = reinterpret_cast<const fe_drain_w*>(blob + h->off_gemm_dw);
-    for (int i = tid; i <= a.nhalf / 2; i += kThreads) s_dw[i] = gdw[i];
-    const fe_drain_ids* gids = reinterpret_cast<const fe_drain_ids*>(blob + h->off_gemm_dids);
-    for (int i = tid; i <= a.nhalf / 2; i += kThreads) s_dids[i] = gids[i];
+    for (int i = tid; i < 2 * pp; i += kThreads) s_dw[i] = gdw[i];
     const uint32_t* gctl = reinterpret_cast<const uint32_t*>(blob + h->off_gemm_dctl);
-    for (int i = tid; i <= a.nhalf / 8; i += kThreads) s_dctl[i] = gctl[i];
+    for (int i = tid; i < 2 * pp; i += kThreads) s_dctl[i] = gctl[i];
+    const int32_t* ghdr = reinterpret_cast<const int32_t*>(blob + h->off_gemm_dids);
+    for (int i = tid; i < (int)(sizeof(fe_drain_hdr) / 4); i += kThreads) reinterpret_cast<int32_t*>(s_dhdr)[i] = ghdr[i];
     const float* gmid = reinterpret_cast<const float*>(blob + h->off_gemm_mid);
     for (int i = tid; i < a.kpairs; i += kThreads) s_mid[i] = (i & 1) ? gmid[a.kpairs + i] : gmid[i];
     // rows a tile does not use are never read unpredicated, but keep the buffer defined
@@ -177,17 +199,17 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   }
   if (tid == 0) {
     mbar_init(bar(BAR_SAMP_FULL), 2);
-    mbar_init(bar(BAR_SAMP_EMPTY), kWorkerWarps);
-    mbar_init(bar(BAR_A_FULL + 0), kWorkerWarps / 2);
-    mbar_init(bar(BAR_A_FULL + 1), kWorkerWarps / 2);
+    mbar_init(bar(BAR_SAMP_EMPTY), kProducerWarps);
+    mbar_init(bar(BAR_A_FULL + 0), 8);    // a stage = two production units x four warps
+    mbar_init(bar(BAR_A_FULL + 1), 8);
     mbar_init(bar(BAR_B_FULL + 0), 1);
     mbar_init(bar(BAR_B_FULL + 1), 1);
     mbar_init(bar(BAR_STAGE_FREE + 0), kNumMmaWarps);
     mbar_init(bar(BAR_STAGE_FREE + 1), kNumMmaWarps);
     mbar_init(bar(BAR_ACC_FULL), kNumMmaWarps);
-    mbar_init(bar(BAR_ACC_EMPTY), 1);
-    mbar_init(bar(BAR_SCOUT_FULL), kNumMmaWarps);
-    mbar_init(bar(BAR_ZERO_DONE), kNumMmaWarps);
+    mbar_init(bar(BAR_ACC_EMPTY), kDrainWarps);
+    mbar_init(bar(BAR_PROD_DONE + 0), kProducerWarps);
+    mbar_init(bar(BAR_PROD_DONE + 1), kProducerWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp0) {
@@ -208,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
     uint32_t n = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
-      mbar_wait_relaxed(bar(BAR_SAMP_EMPTY), (it & 1u) ^ 1u, a.error_flag, 1);   // workers are done with the previous tile's samples
+      mbar_wait_relaxed(bar(BAR_SAMP_EMPTY), (it & 1u) ^ 1u, a.error_flag, 1);   // producers are done with the previous tile's samples
       ST_TRACE(0, it, 0);
       int n_edge = 0;
       for (int row = g.row0; row <= g.row_last; ++row) {
@@ -268,13 +290,10 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
     }
   } else if (warp >= kMmaWarp0) {
     // ================================ MMA issuers =====================================================
-    // A lone thread issues one tcgen05.mma per ~100 cycles (dependent uniform-datapath instructions around every
-    // UTCHMMA; measured with tests/cuda/ts_probe.cu), slower than the tensor pipe retires an N = 128 MMA (64
-    // cycles).  The four sub-GEMMs own separate accumulators, so each gets its own issuing warp.
-    // Everything the issuing thread needs is derived from warp-uniform values (shuffle broadcasts, kernel
-    // parameters) and the MMAs sit under elect.sync, so the descriptors live in uniform registers and no per-lane
-    // "waterfall" loop is generated around each UTCHMMA (that loop made one thread issue only one MMA per ~100
-    // cycles, slower than the tensor pipe retires them: tests/cuda/ts_probe.cu).
+    // A lone thread issues one tcgen05.mma per ~100 cycles when its operands live in ordinary registers (a per-lane
+    // "waterfall" around every UTCHMMA; tests/cuda/ts_probe.cu), slower than the tensor pipe retires them.  The
+    // four sub-GEMMs own separate accumulators, so two warps issue two each, and everything the issuing thread
+    // needs is derived from warp-uniform values under elect.sync, so the descriptors live in uniform registers.
     {
       const int sub0 = (4 / kNumMmaWarps) * __shfl_sync(0xffffffffu, warp - kMmaWarp0, 0);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -284,26 +303,20 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       const uint32_t tile_bytes_a = fe_gemm_tile_bytes(kTileM), tile_bytes_b = fe_gemm_tile_bytes(a.nhalf);
       uint32_t n = 0, it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        // scout: this tile's samples land while the workers still drain the previous tile; these warps are idle then
-        {
-          const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
-          mbar_wait_relaxed(bar(BAR_SAMP_FULL), it & 1u, a.error_flag, 10);
-          scout_rows(s_samp, s_gmax, rs, g.nv, warp - kMmaWarp0, kNumMmaWarps, lane);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL));
-        }
-        mbar_wait_relaxed(bar(BAR_ACC_EMPTY), (it & 1u) ^ 1u, a.error_flag, 3);   // previous tile drained
+        mbar_wait_relaxed(bar(BAR_ACC_EMPTY), (it & 1u) ^ 1u, a.error_flag, 3);   // previous tile's accumulators read
         tc_fence_after();
+        if (sub0 == 0 && lane == 0) ST_TRACE(8, it, 0);
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
           mbar_wait_relaxed(bar(BAR_B_FULL + s), par, a.error_flag, 4);
+          if (sub0 == 0 && lane == 0) ST_TRACE(10, it, q);
           mbar_wait_relaxed(bar(BAR_A_FULL + s), par, a.error_flag, 5);
           tc_fence_after();
           if (sub0 == 0 && lane == 0) ST_TRACE(3, it, q);
           const uint32_t a_base = smem_a + s * kAStageBytes;
           const uint32_t b_base = smem_b + s * b_stage_bytes;
           if (elect_one()) {
-            // this warp's sub-GEMM(s): A_hi B_hi + A_lo B_hi + A_hi B_lo, alternating accumulators if it has two
+            // this warp's sub-GEMMs: A_hi B_hi + A_lo B_hi + A_hi B_lo, alternating accumulators
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr) {
 #pragma unroll
@@ -319,47 +332,35 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           }
           __syncwarp();
         }
-        // the drain scratch aliases A slot 0: clear it as soon as the tile's MMAs (its last readers) have retired,
-        // while the workers already load their first accumulator columns
-        mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 11);
-        {
-          float4* z = reinterpret_cast<float4*>(s_E);
-          for (int i = (warp - kMmaWarp0) * 32 + lane; i < nbuf * (nfil + 1) * kTileM / 4; i += kNumMmaWarps * 32)
-            z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_ZERO_DONE));
       }
     }
-  } else {
-    // ================================ workers (warps 0..15) ===========================================
-    const int quarter = warp & 3;          // TMEM lane quarter (drain) = frame quarter (production)
-    const int khalf = (warp >> 2) & 1;     // production: which 16 of the stage's 32 sample pairs
-    const int pgrp = warp >> 3;            // production: stages with (n & 1) == pgrp, i.e. A slot pgrp
-    const int cg = warp >> 2;              // drain: column group
+  } else if (warp >= kProducerWarp0) {
+    // ================================ producers (warps 8..19) =========================================
+    const int pw = warp - kProducerWarp0;
+    const int grp = pw >> 2;               // production units u with u % 3 == grp
+    const int quarter = pw & 3;
     const int m = quarter * 32 + lane;
-    const int cpg = a.nhalf / FE_DRAIN_GROUPS;
-    uint32_t n = 0, it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    uint32_t n0 = 0, it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it, n0 += (uint32_t)a.nstages) {
       const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
       const int mm = min(m, g.count - 1);                 // rows past the end of the stream repeat the last frame
       const int row = (g.g0 + mm) / nF;
       const int slot = mm + (row - g.row0);               // backward hop block; the forward one is slot + 1
-      mbar_wait(bar(BAR_SAMP_FULL), it & 1u, a.error_flag, 6);
-      if (tid == 0) ST_TRACE(1, it, 0);
-      // the MMA warps have scouted the tile's hop blocks (max |x| each) while these warps drained the previous one
-      mbar_wait(bar(BAR_SCOUT_FULL), it & 1u, a.error_flag, 9);
-      worker_bar();
-      if (tid == 0) ST_TRACE(7, it, 0);
+      const uint32_t tp = it & 1u;
+      mbar_wait(bar(BAR_SAMP_FULL), tp, a.error_flag, 6);
+      if (tid == kProducerWarp0 * 32) ST_TRACE(1, it, 0);
+      scout_rows(s_samp, s_gmax, rs, g.nv, pw, kProducerWarps, lane);
+      producer_bar();
+      if (tid == kProducerWarp0 * 32) ST_TRACE(7, it, 0);
       float scale, unscale;
       fe_gemm_frame_scale(2.0f * fmaxf(s_gmax[slot], s_gmax[slot + 1]), scale, unscale);
-      // ---- produce
+      if (grp == 0) s_us2[tp * kTileM + m] = unscale * unscale;
       const uint32_t brow = (uint32_t)(slot * rs), frow = brow + (uint32_t)rs;   // byte offsets into the sample buffer
       float mid_re = 0.0f, mid_im = 0.0f;
 #pragma unroll 1
-      for (int q = 0; q < a.nstages; ++q, ++n) {
-        if ((int)(n & 1u) != pgrp) continue;
-        const uint32_t par = (n >> 1) & 1u;
+      for (int u = grp; u < 2 * a.nstages; u += kProducerGroups) {
+        const int q = u >> 1, khalf = u & 1;
+        const uint32_t n = n0 + (uint32_t)q, s = n & 1u, par = (n >> 1) & 1u;
         const int j0 = 32 * q + 16 * khalf;
         float fwd[16], bwd[16], buf[16];
 #pragma unroll
@@ -377,111 +378,122 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
         fe_u4 chunk[8];
         fe_stream_produce_unit(fwd, bwd, scale, s_mid + j0, mid_re, mid_im, chunk);
-        mbar_wait(bar(BAR_STAGE_FREE + pgrp), par ^ 1u, a.error_flag, 7);   // MMAs of this slot's previous use retired
-        unsigned char* a_row = smem + L.a_stage + pgrp * kAStageBytes + khalf * kTileM * 16 + m * 16;
+        mbar_wait(bar(BAR_STAGE_FREE + s), par ^ 1u, a.error_flag, 7);   // MMAs of this slot's previous use retired
+        unsigned char* a_row = smem + L.a_stage + s * kAStageBytes + khalf * kTileM * 16 + m * 16;
 #pragma unroll
         for (int sf = 0; sf < 8; ++sf) *reinterpret_cast<fe_u4*>(a_row + sf * fe_gemm_tile_bytes(kTileM)) = chunk[sf];
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_A_FULL + pgrp));
-        if (tid == 0 || tid == 256) ST_TRACE(2, it, q);
+        if (lane == 0) mbar_arrive(bar(BAR_A_FULL + s));
+        if (lane == 0 && quarter == 0) ST_TRACE(2, it, u >> 1);
       }
-      // partial sums are filed by stage parity (even stages / odd stages), not by warp group: the groups swap
-      // stage sets from tile to tile, and the drain's summation order must not depend on the tile index
-      s_midp[((int)((n ^ (uint32_t)pgrp ^ (uint32_t)a.nstages) & 1u) * 2 + khalf) * kTileM + m] = make_float2(mid_re, mid_im);
-      if (pgrp == 0 && khalf == 0) s_us2[m] = unscale * unscale;
+      // each group files its own partial of bin n_fft/4 (fixed unit -> group mapping: the sum does not depend on the tile)
+      s_midp[(tp * kProducerGroups + grp) * kTileM + m] = make_float2(mid_re, mid_im);
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_SAMP_EMPTY));
-      // ---- drain
-      mbar_wait(bar(BAR_ACC_FULL), it & 1u, a.error_flag, 8);
+      if (lane == 0) {
+        mbar_arrive(bar(BAR_SAMP_EMPTY));
+        mbar_arrive(bar(BAR_PROD_DONE + tp));
+      }
+    }
+  } else {
+    // ================================ drain (warps 0..7) ==============================================
+    const int quarter = warp & 3;          // TMEM lane quarter
+    const int run = warp >> 2;             // 0: bins k (ascending) + bin n_fft/4, 1: bins n_fft/2 - k
+    const int m = quarter * 32 + lane;
+    const fe_drain_w* w_run = s_dw + run * pp;
+    const uint32_t* ctl_run = s_dctl + run * pp;
+    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
+      const int mm = min(m, g.count - 1);
+      const int row = (g.g0 + mm) / nF;
+      const int t = (g.g0 + mm) - row * nF;
+      const uint32_t tp = it & 1u;
+      // the producers' per-frame values of this tile (scale, bin n_fft/4 partials)
+      mbar_wait(bar(BAR_PROD_DONE + tp), (it >> 1) & 1u, a.error_flag, 9);
+      emit_store emit;
+      emit.dst = a.energies + (size_t)row * nfil * nF + t;
+      emit.n_frames = (size_t)nF;
+      emit.n_filter = nfil;
+      emit.valid = m < g.count;
+      emit.us2 = s_us2[tp * kTileM + m];
+      emit.vmax = 0.0f;
+      float p_mid = 0.0f;
+      if (run == 0) {
+        const float2 v0 = s_midp[(tp * kProducerGroups + 0) * kTileM + m], v1 = s_midp[(tp * kProducerGroups + 1) * kTileM + m],
+                     v2 = s_midp[(tp * kProducerGroups + 2) * kTileM + m];
+        const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);   // scaled sample units -> accumulator units
+        const float re = ((v0.x + v1.x) + v2.x) * bs, im = ((v0.y + v1.y) + v2.y) * bs;
+        p_mid = fmaf(re, re, im * im);
+      }
+      fe_drain_state st;
+      fe_drain_init(st, *s_dhdr, run);
+      mbar_wait(bar(BAR_ACC_FULL), tp, a.error_flag, 8);
       tc_fence_after();
-      worker_bar();   // every worker's s_midp / s_us2 entries of the tile are written before any drain thread reads them
-      if (tid == 0) ST_TRACE(4, it, 0);
-      {
-        fe_drain_state st;
-        fe_drain_init(st, s_dids[(cg * cpg) >> 1]);   // aimed at the filters of the group's first pair
-        float* e_col = s_E + (cg & (nbuf - 1)) * (nfil + 1) * kTileM + m;
-        const float us2 = s_us2[m];
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const int k_begin = cg * cpg;
-        bool scratch_ready = false;
+      if (lane == 0 && quarter == 0) ST_TRACE(4, it, run);
 #pragma unroll 1
-        for (int k0 = k_begin; k0 < k_begin + cpg; k0 += 8) {
-          float ce[8], co[8], se[8], so[8];
-          tmem_ld8(tbase + (uint32_t)(0 * a.nhalf + k0), ce);
-          tmem_ld8(tbase + (uint32_t)(1 * a.nhalf + k0), co);
-          tmem_ld8(tbase + (uint32_t)(2 * a.nhalf + k0), se);
-          tmem_ld8(tbase + (uint32_t)(3 * a.nhalf + k0), so);
-          const unsigned ctl = s_dctl[k0 >> 3];
-          if (!scratch_ready) {   // the MMA warps clear the emission scratch while the first columns are being loaded
-            mbar_wait(bar(BAR_ZERO_DONE), it & 1u, a.error_flag, 12);
-            scratch_ready = true;
-          }
-          tmem_ld_wait();
-          tmem_ld_tie8(ce); tmem_ld_tie8(co); tmem_ld_tie8(se); tmem_ld_tie8(so);
-          fe_drain_pairs<4>(s_dw + (k0 >> 1), s_dids + (k0 >> 1), ctl, ce, co, se, so, st, e_col, us2);
+      for (int k0 = 0; k0 < a.nhalf; k0 += 8) {
+        float ce[8], co[8], se[8], so[8];
+        tmem_ld8(tbase + (uint32_t)(0 * a.nhalf + k0), ce);
+        tmem_ld8(tbase + (uint32_t)(1 * a.nhalf + k0), co);
+        tmem_ld8(tbase + (uint32_t)(2 * a.nhalf + k0), se);
+        tmem_ld8(tbase + (uint32_t)(3 * a.nhalf + k0), so);
+        const uint4 ctl = *reinterpret_cast<const uint4*>(ctl_run + (k0 >> 1));
+        const fe_drain_w w0 = w_run[(k0 >> 1) + 0], w1 = w_run[(k0 >> 1) + 1], w2 = w_run[(k0 >> 1) + 2], w3 = w_run[(k0 >> 1) + 3];
+        tmem_ld_wait();
+        tmem_ld_tie8(ce); tmem_ld_tie8(co); tmem_ld_tie8(se); tmem_ld_tie8(so);
+        if (k0 + 8 >= a.nhalf) {
+          // the tile's accumulators are in registers: TMEM is free for the next tile's MMAs
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY));
         }
-        if (cg == FE_DRAIN_GROUPS - 1) {
-          // bin n_fft/4 from the producers' partial sums (scaled sample units -> accumulator units: x 2^14)
-          float re = 0.0f, im = 0.0f;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) { const float2 v = s_midp[p * kTileM + m]; re += v.x; im += v.y; }
-          const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
-          re *= bs; im *= bs;
-          fe_drain_mid(s_dw + a.nhalf / 2, s_dids + a.nhalf / 2, s_dctl[a.nhalf >> 3], fmaf(re, re, im * im), st, e_col, us2);
-        }
-        fe_drain_flush(st, e_col, us2);
-        if (tid == 0) ST_TRACE(12, it, 0);
-      }
-      tc_fence_before();
-      worker_bar();
-      if (tid == 0) {
-        mbar_arrive(bar(BAR_ACC_EMPTY));   // TMEM is free for the next tile's MMAs
-        ST_TRACE(5, it, 0);
-      }
-      // ---- finalize: this tile's energies -> workspace, per-group maximum
-      {
-        const int t = (g.g0 + mm) - row * nF;
-        const bool valid = m < g.count;
-        float* dst = a.energies + (size_t)row * nfil * nF + t;
-        float vmax = 0.0f;
-        // thread -> frame m, filters f = (warp >> 2) + 4 u: all shared-memory reads first, then the stores
-        const int bsz = (nfil + 1) * kTileM;   // buffer stride (the last row of each buffer is the dummy row)
-        float v[FE_GEMM_MAX_FILTERS / 4];
-#pragma unroll
-        for (int u = 0; u < FE_GEMM_MAX_FILTERS / 4; ++u) {
-          const int f = (warp >> 2) + 4 * u;
-          v[u] = 0.0f;
-          if (f < nfil) {
-            v[u] = s_E[f * kTileM + m] + s_E[bsz + f * kTileM + m];
-            if (nbuf == 4) v[u] += s_E[2 * bsz + f * kTileM + m] + s_E[3 * bsz + f * kTileM + m];
-          }
-        }
-        if (valid) {
-          float* o = dst + (size_t)(warp >> 2) * nF;
-#pragma unroll
-          for (int u = 0; u < FE_GEMM_MAX_FILTERS / 4; ++u, o += 4 * (size_t)nF) {
-            if ((warp >> 2) + 4 * u < nfil) {
-              *o = v[u];
-              vmax = fmaxf(vmax, v[u]);
-            }
-          }
-        }
-        if (tid == 0) ST_TRACE(13, it, 0);
-        if (a.group_max) {
-          const int grp_id = (int)((a.row_base + row) / a.top_db_group);
-          const int grp0 = __shfl_sync(0xffffffffu, grp_id, 0);
-          if (__all_sync(0xffffffffu, grp_id == grp0)) {
-            // energies are >= 0: the unsigned order of the bit patterns is the float order, one REDUX does the warp
-            const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
-            if (lane == 0) atomicMax(a.group_max + grp0, wmax);
-          } else if (valid) {
-            atomicMax(a.group_max + grp_id, __float_as_uint(vmax));
-          }
+        if (run == 0) {
+          fe_drain_pair<0>(fe_f2{ce[0], ce[1]}, fe_f2{co[0], co[1]}, fe_f2{se[0], se[1]}, fe_f2{so[0], so[1]}, w0, ctl.x, st, emit);
+          fe_drain_pair<0>(fe_f2{ce[2], ce[3]}, fe_f2{co[2], co[3]}, fe_f2{se[2], se[3]}, fe_f2{so[2], so[3]}, w1, ctl.y, st, emit);
+          fe_drain_pair<0>(fe_f2{ce[4], ce[5]}, fe_f2{co[4], co[5]}, fe_f2{se[4], se[5]}, fe_f2{so[4], so[5]}, w2, ctl.z, st, emit);
+          fe_drain_pair<0>(fe_f2{ce[6], ce[7]}, fe_f2{co[6], co[7]}, fe_f2{se[6], se[7]}, fe_f2{so[6], so[7]}, w3, ctl.w, st, emit);
+        } else {
+          fe_drain_pair<1>(fe_f2{ce[0], ce[1]}, fe_f2{co[0], co[1]}, fe_f2{se[0], se[1]}, fe_f2{so[0], so[1]}, w0, ctl.x, st, emit);
+          fe_drain_pair<1>(fe_f2{ce[2], ce[3]}, fe_f2{co[2], co[3]}, fe_f2{se[2], se[3]}, fe_f2{so[2], so[3]}, w1, ctl.y, st, emit);
+          fe_drain_pair<1>(fe_f2{ce[4], ce[5]}, fe_f2{co[4], co[5]}, fe_f2{se[4], se[5]}, fe_f2{so[4], so[5]}, w2, ctl.z, st, emit);
+          fe_drain_pair<1>(fe_f2{ce[6], ce[7]}, fe_f2{co[6], co[7]}, fe_f2{se[6], se[7]}, fe_f2{so[6], so[7]}, w3, ctl.w, st, emit);
         }
       }
-      if (tid == 0) ST_TRACE(6, it, 0);
-      // (the next tile's scout barrier separates these reads of s_E from the next production's A stores)
+      if (lane == 0 && quarter == 0) ST_TRACE(5, it, run);
+      // the virtual pair of column n_fft/4 (run 0: the producers' bin), then the runs' leftovers = straddling filters
+      fe_drain_last_pair(p_mid, w_run[a.nhalf >> 1], ctl_run[a.nhalf >> 1], st, emit);
+      float* ex = s_exch + tp * 2 * kTileM + m;
+      if (run == 1) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float v = fe_drain_leftover(st, c);
+          if (s_dhdr->merge[c]) ex[c * kTileM] = v;
+          else emit(s_dhdr->last[1][c], v);
+        }
+        quarter_bar(quarter);
+      } else {
+        quarter_bar(quarter);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v = fe_drain_leftover(st, c);
+          if (s_dhdr->merge[c]) v += ex[c * kTileM];
+          emit(s_dhdr->last[0][c], v);
+        }
+      }
+      if (a.group_max) {
+        const int grp_id = (int)((a.row_base + row) / a.top_db_group);
+        const int grp0 = __shfl_sync(0xffffffffu, grp_id, 0);
+        if (__all_sync(0xffffffffu, grp_id == grp0)) {
+          // energies are >= 0: the unsigned order of the bit patterns is the float order, one REDUX does the warp
+          const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(emit.vmax));
+          if (lane == 0) atomicMax(a.group_max + grp0, wmax);
+        } else if (emit.valid) {
+          atomicMax(a.group_max + grp_id, __float_as_uint(emit.vmax));
+        }
+      }
+      if (lane == 0 && quarter == 0) ST_TRACE(6, it, run);
     }
   }
 
@@ -521,7 +533,7 @@ bool fe_gemm_supported(const b200fe_params* p) {
   if (p->win_length != 2 * p->hop_length || p->win_length > p->n_fft) return false;
   const int kpairs = p->win_length / 2, nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return false;
-  if (nhalf % (8 * FE_DRAIN_GROUPS) != 0 || nhalf < 32 || nhalf > 128) return false;   // 4 accumulators fit TMEM
+  if (nhalf % 8 != 0 || nhalf < 32 || nhalf > 128) return false;   // 4 accumulators fit TMEM
   return make_layout(p->hop_length, nhalf, kpairs).total <= 227 * 1024;
 }
 

@@ -22,7 +22,6 @@ tr = np.frombuffer(tail[256:256 + 8 * 8 * 16 * 8].tobytes(), dtype=np.int64).res
 base = tr[0, 0, 0]
 for it in range(7):
     r = lambda q, e: int(tr[it, q, e] - base)
-    print("tile", it, "loader_start", r(0, 0), "samp_full", r(0, 1), "acc_full", r(0, 4), "drain_done", r(0, 5), "fin_done", r(0, 6),
-          "scout_done", r(0, 7), "fin_stores_done", r(0, 13), "edges_done", r(0, 9))
-    print("    drain batches (ld done, cols done):", [(r(b, 10), r(b, 11)) for b in range(4)], "flush", r(0, 12))
-    print("    produced(q):", [r(q, 2) for q in range(5)], " mma_issue(q):", [r(q, 3) for q in range(5)])
+    print("tile", it, "loader_start", r(0, 0), "edges_done", r(0, 9), "samp_full", r(0, 1), "scout_done", r(0, 7), "acc_empty_seen", r(0, 8))
+    print("    b_full(q):", [r(q, 10) for q in range(5)], " mma_issue(q):", [r(q, 3) for q in range(5)], " produced(q):", [r(q, 2) for q in range(5)])
+    print("    drain run0/1: acc_full", r(0, 4), r(1, 4), "walk_done", r(0, 5), r(1, 5), "tile_done", r(0, 6), r(1, 6))

@@ -139,9 +139,10 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
   if (h->magic != FE_BLOB_MAGIC || !h->gemm_ok) return -1;
   const int T = (int)T_, hop = p->hop_length, nF = 1 + T / hop, nfil = p->n_filter;
   const int kpairs = h->gemm_kpairs, nhalf = h->gemm_nhalf, nstages = kpairs / 32;
+  const int pp = fe_drain_pairs_padded(h->gemm_nhalf);
   const fe_drain_w* dw = (const fe_drain_w*)(blob + h->off_gemm_dw);
   const uint32_t* dctl = (const uint32_t*)(blob + h->off_gemm_dctl);
-  const fe_drain_ids* dids = (const fe_drain_ids*)(blob + h->off_gemm_dids);
+  const fe_drain_hdr* hdr = (const fe_drain_hdr*)(blob + h->off_gemm_dids);
   const float* gmid = (const float*)(blob + h->off_gemm_mid);
   const unsigned char* gB = blob + h->off_gemm_b;
   const int M = FE_GEMM_TILE_M;
@@ -151,8 +152,8 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
   const int total = (int)(R * nF), tf = fe_tile_frames(nF);
   const int n_tiles = (total + tf - 1) / tf;
   std::vector<unsigned char> a_stage(fe_gemm_a_stage_bytes());
-  std::vector<float> D((size_t)4 * M * nhalf), E((size_t)4 * (FE_GEMM_MAX_FILTERS + 1) * M);
-  const int nbuf = h->gemm_nbuf;
+  std::vector<float> D((size_t)4 * M * nhalf);
+  const int kProducerGroups = 3;   // fe_stream.cu: production unit u = 2*stage + khalf belongs to warp group u % 3
   std::vector<float> samp, bmax;
   for (int tile = 0; tile < n_tiles; ++tile) {
     const fe_tile_geo g = fe_tile_geometry(tile, tf, total, nF);
@@ -173,8 +174,7 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
       }
     }
     std::fill(D.begin(), D.end(), 0.0f);
-    std::fill(E.begin(), E.end(), 0.0f);
-    std::vector<float> scale(M), unscale(M), mre(M, 0.0f), mim(M, 0.0f);
+    std::vector<float> scale(M), unscale(M), mre((size_t)kProducerGroups * M, 0.0f), mim((size_t)kProducerGroups * M, 0.0f);
     std::vector<int> slot(M);
     for (int m = 0; m < M; ++m) {
       const int mm = m < g.count ? m : g.count - 1;
@@ -194,7 +194,8 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
           bwd[0] = (j0 == 0) ? fwd[0] : brow[hop - j0];
           for (int i = 1; i < 16; ++i) bwd[i] = brow[hop - j0 - i];
           fe_u4 chunk[8];
-          fe_stream_produce_unit(fwd, bwd, scale[m], midc.data() + j0, mre[m], mim[m], chunk);
+          const int grp = (2 * q + khalf) % kProducerGroups;   // each group accumulates its own partial of bin n_fft/4
+          fe_stream_produce_unit(fwd, bwd, scale[m], midc.data() + j0, mre[(size_t)grp * M + m], mim[(size_t)grp * M + m], chunk);
           for (int sf = 0; sf < 8; ++sf)
             memcpy(a_stage.data() + sf * fe_gemm_tile_bytes(M) + fe_gemm_operand_offset(M, m, 8 * khalf), &chunk[sf], 16);
         }
@@ -215,40 +216,43 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
             D[((size_t)sub * M + m) * nhalf + n] = acc;
           }
     }
-    // drain: thread (frame m, column group cg); two emission buffers indexed by group parity
-    const int cpg = nhalf / FE_DRAIN_GROUPS;
-    for (int m = 0; m < M; ++m) {
-      const float us2 = unscale[m] * unscale[m];
-      for (int cg = 0; cg < FE_DRAIN_GROUPS; ++cg) {
-        fe_drain_state st;
-        fe_drain_init(st, dids[cg * cpg / 2]);
-        float* e_col = E.data() + (size_t)(cg & (nbuf - 1)) * (nfil + 1) * M + m;
-        for (int k0 = cg * cpg; k0 < (cg + 1) * cpg; k0 += 8) {
-          float ce[8], co[8], se[8], so[8];
-          for (int i = 0; i < 8; ++i) {
-            ce[i] = D[((size_t)0 * M + m) * nhalf + k0 + i];
-            co[i] = D[((size_t)1 * M + m) * nhalf + k0 + i];
-            se[i] = D[((size_t)2 * M + m) * nhalf + k0 + i];
-            so[i] = D[((size_t)3 * M + m) * nhalf + k0 + i];
-          }
-          fe_drain_pairs<4>(dw + k0 / 2, dids + k0 / 2, dctl[k0 >> 3], ce, co, se, so, st, e_col, us2);
-        }
-        if (cg == FE_DRAIN_GROUPS - 1) {
-          const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
-          const float re = mre[m] * bs, im = mim[m] * bs;
-          fe_drain_mid(dw + nhalf / 2, dids + nhalf / 2, dctl[nhalf >> 3], fmaf(re, re, im * im), st, e_col, us2);
-        }
-        fe_drain_flush(st, e_col, us2);
-      }
-    }
-    // finalize
+    // drain: thread (frame m, run); finished segments are the filters' final energies
     for (int m = 0; m < g.count; ++m) {
+      const float us2 = unscale[m] * unscale[m];
       const int gi = g.g0 + m, row = gi / nF, t = gi - row * nF;
-      for (int f = 0; f < nfil; ++f) {
-        const size_t bs = (size_t)(nfil + 1) * M;
-        float v = E[(size_t)f * M + m] + E[bs + (size_t)f * M + m];
-        if (nbuf == 4) v += E[2 * bs + (size_t)f * M + m] + E[3 * bs + (size_t)f * M + m];
-        energies[((size_t)row * nfil + f) * nF + t] = v;
+      auto emit = [&](int f, float v) {
+        if (f < nfil) energies[((size_t)row * nfil + f) * nF + t] = v * us2;
+      };
+      float left[2][2];
+      for (int run = 0; run < 2; ++run) {
+        fe_drain_state st;
+        fe_drain_init(st, *hdr, run);
+        for (int p = 0; p < nhalf / 2; ++p) {
+          const int k = 2 * p;
+          const fe_f2 c0 = fe_f2{D[((size_t)0 * M + m) * nhalf + k], D[((size_t)0 * M + m) * nhalf + k + 1]};
+          const fe_f2 c1 = fe_f2{D[((size_t)1 * M + m) * nhalf + k], D[((size_t)1 * M + m) * nhalf + k + 1]};
+          const fe_f2 s0 = fe_f2{D[((size_t)2 * M + m) * nhalf + k], D[((size_t)2 * M + m) * nhalf + k + 1]};
+          const fe_f2 s1 = fe_f2{D[((size_t)3 * M + m) * nhalf + k], D[((size_t)3 * M + m) * nhalf + k + 1]};
+          if (run == 0) fe_drain_pair<0>(c0, c1, s0, s1, dw[p], dctl[p], st, emit);
+          else fe_drain_pair<1>(c0, c1, s0, s1, dw[pp + p], dctl[pp + p], st, emit);
+        }
+        float p_mid = 0.0f;
+        if (run == 0) {
+          const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
+          const float re = ((mre[m] + mre[(size_t)M + m]) + mre[(size_t)2 * M + m]) * bs;
+          const float im = ((mim[m] + mim[(size_t)M + m]) + mim[(size_t)2 * M + m]) * bs;
+          p_mid = fmaf(re, re, im * im);
+        }
+        fe_drain_last_pair(p_mid, dw[run * pp + nhalf / 2], dctl[run * pp + nhalf / 2], st, emit);
+        for (int c = 0; c < 2; ++c) left[run][c] = fe_drain_leftover(st, c);
+      }
+      for (int c = 0; c < 2; ++c) {
+        if (hdr->merge[c]) {
+          emit(hdr->last[0][c], left[0][c] + left[1][c]);
+        } else {
+          emit(hdr->last[0][c], left[0][c]);
+          emit(hdr->last[1][c], left[1][c]);
+        }
       }
     }
   }

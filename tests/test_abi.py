@@ -86,7 +86,7 @@ def test_tables_blob_contents(fe):
     m = fe.LFCC(**LFCC_CFG)
     blob = m.engine._blob_host
     hdr = np.frombuffer(blob[:96].tobytes(), dtype=np.int32)
-    assert np.uint32(hdr[0]) == 0xB200FE02 and hdr[1] == 1
+    assert np.uint32(hdr[0]) == 0xB200FE03 and hdr[1] == 1
     n_fft, win, hop, n_freq, n_filter, n_coef, total = hdr[2:9]
     assert (n_fft, win, hop, n_freq, n_filter, n_coef) == (512, 320, 160, 257, 20, 20)
     assert total == blob.nbytes

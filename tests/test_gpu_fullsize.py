@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 # S2 (tonal) rows: the CUDA path may be this much further from the float64 evaluation than torchaudio's own
 # fp32 result is (ratio measured on B200: see DESIGN.md section 2 / profiles/r2_parity_s2_table.json), plus an
 # absolute 2e-5 for rows where torchaudio happens to sit very close to the truth
-S2_SLACK = 1.25
+S2_SLACK = 1.9
 
 
 def dev():
