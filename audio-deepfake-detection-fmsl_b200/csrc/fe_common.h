@@ -44,11 +44,11 @@ struct fe_blob_header {
   int32_t off_gemm_b;      // __half operand tiles, see fe_gemm_layout.h
   int32_t gemm_b_bytes;
   int32_t off_gemm_mid;    // float[2][gemm_kpairs]  true-unit weights of bin n_fft/4 (Re from a_e, Im from a_o)
-  // sliding even/odd filter accumulators of the drain (fe_gemm_layout.h); PP = fe_drain_pairs_padded(gemm_nhalf)
-  int32_t off_gemm_dw;     // fe_drain_w[2 runs][PP]   per column pair (+ the virtual pair of column n_fft/4): weights
-  int32_t off_gemm_dctl;   // uint32[2 runs][PP]       per pair: switch codes and new targets
-  int32_t off_gemm_dids;   // fe_drain_hdr             first / last targets of the runs, straddler merge flags
-  int32_t gemm_nbuf;       // (unused since the drain stores final energies directly; kept for layout stability)
+  // sliding even/odd filter accumulators of the drain (fe_gemm_layout.h)
+  int32_t off_gemm_dw;     // fe_drain_w[2 runs][nhalf/2]        per column pair: weights of the segment active at the batch start
+  int32_t off_gemm_dctl;   // uint32[2 runs][nhalf/8]            per batch: boundary flags and new targets
+  int32_t off_gemm_dids;   // fe_drain_hdr                       first / last targets of the runs, straddler merge flags
+  int32_t off_gemm_dwn;    // float[2 runs][nhalf/8][2][4][2]    per batch and class: weights behind the boundary (pair, half)
   int32_t reserved[6];
 };
 

@@ -181,60 +181,73 @@ FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scal
 // ---- drain: sliding even/odd filter accumulators over column pairs (tables and protocol: fe_gemm_layout.h) ---------
 struct fe_drain_state {
   fe_f2 acc[2];    // class = filter parity: .x even columns, .y odd columns
-  float pend[2];   // odd-column part of a segment whose even half has not switched yet
   int tgt[2];      // filter the class is aimed at (FE_DRAIN_NONE: none)
+  float defer[2];  // half 1: right part of the segment that straddles the halves (stored once half 0's part is known)
 };
 
-FE_HD void fe_drain_init(fe_drain_state& st, const fe_drain_hdr& hdr, int run) {
+FE_HD void fe_drain_init(fe_drain_state& st, const fe_drain_hdr& hdr, int run, int half) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     st.acc[c] = fe_f2{0.0f, 0.0f};
-    st.pend[c] = 0.0f;
-    st.tgt[c] = hdr.first[run][c];
+    st.tgt[c] = hdr.first[run][half][c];
+    st.defer[c] = 0.0f;
   }
 }
 
-// the (thread-uniform) switches of one pair; `emit(filter, value)` receives a finished segment (scaled units)
-template <class Emit>
-FE_HD void fe_drain_switch(unsigned ctl, fe_drain_state& st, Emit& emit) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    if (ctl & (1u << (2 * c))) {
-      st.pend[c] = st.acc[c].y;
-      st.acc[c].y = 0.0f;
-    }
-    if (ctl & (2u << (2 * c))) {
-      emit(st.tgt[c], st.acc[c].x + st.pend[c]);
-      st.acc[c].x = 0.0f;
-      st.pend[c] = 0.0f;
-      st.tgt[c] = (int)((ctl >> (8 + 8 * c)) & 255u);
-    }
-  }
-}
-
-// One column pair of run RUN: |X[k]|^2 = (ce+co)^2 + (se+so)^2 (run 0) or |X[n_fft/2 - k]|^2 = (ce-co)^2 + (so-se)^2
-// (run 1) for the two columns at a time, then the two classes' weighted sums.
-template <int RUN, class Emit>
-FE_HD void fe_drain_pair(fe_f2 c0, fe_f2 c1, fe_f2 s0, fe_f2 s1, const fe_drain_w& w, unsigned ctl, fe_drain_state& st,
-                         Emit& emit) {
+// Powers of one column pair of run RUN: |X[k]|^2 = (ce+co)^2 + (se+so)^2 (run 0) or
+// |X[n_fft/2 - k]|^2 = (ce-co)^2 + (so-se)^2 (run 1), two columns at a time.
+template <int RUN>
+FE_HD fe_f2 fe_drain_power(fe_f2 c0, fe_f2 c1, fe_f2 s0, fe_f2 s1) {
   const fe_f2 neg = fe_f2{-1.0f, -1.0f};
   const fe_f2 re = RUN == 0 ? fe_add2(c0, c1) : fe_fma2(c1, neg, c0);
   const fe_f2 im = RUN == 0 ? fe_add2(s0, s1) : fe_fma2(s0, neg, s1);
-  const fe_f2 pw = fe_fma2(re, re, fe_mul2(im, im));
-  if (ctl & 15u) fe_drain_switch(ctl, st, emit);
-  st.acc[0] = fe_fma2(pw, fe_f2{w.w[0][0], w.w[0][1]}, st.acc[0]);
-  st.acc[1] = fe_fma2(pw, fe_f2{w.w[1][0], w.w[1][1]}, st.acc[1]);
+  return fe_fma2(re, re, fe_mul2(im, im));
 }
 
-// the virtual pair of column n_fft/4: run 0 adds the producers' bin (power p_mid, even half), run 1 only switches
+// One batch of 4 column pairs: the classes' weighted sums, then (thread-uniform) the segment ends of the batch:
+// `emit(filter, value)` receives a finished segment (scaled units), the class carries on with the sum of the columns
+// behind the boundary.  wn = this batch's [class][pair][half] weights behind the boundaries.
 template <class Emit>
-FE_HD void fe_drain_last_pair(float p_mid, const fe_drain_w& w, unsigned ctl, fe_drain_state& st, Emit& emit) {
-  if (ctl & 15u) fe_drain_switch(ctl, st, emit);
-  st.acc[0].x = fmaf(p_mid, w.w[0][0], st.acc[0].x);
-  st.acc[1].x = fmaf(p_mid, w.w[1][0], st.acc[1].x);
+FE_HD void fe_drain_batch(const fe_f2* pw, const fe_drain_w* w, const float* wn, unsigned ctl, fe_drain_state& st, Emit& emit) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    st.acc[0] = fe_fma2(pw[p], fe_f2{w[p].w[0][0], w[p].w[0][1]}, st.acc[0]);
+    st.acc[1] = fe_fma2(pw[p], fe_f2{w[p].w[1][0], w[p].w[1][1]}, st.acc[1]);
+  }
+  if (ctl & 3u) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (ctl & (1u << c)) {
+        fe_f2 nx = fe_mul2(pw[0], fe_f2{wn[c * 8 + 0], wn[c * 8 + 1]});
+#pragma unroll
+        for (int p = 1; p < 4; ++p) nx = fe_fma2(pw[p], fe_f2{wn[c * 8 + 2 * p], wn[c * 8 + 2 * p + 1]}, nx);
+        if (ctl & (4u << c)) st.defer[c] = st.acc[c].x + st.acc[c].y;
+        else emit(st.tgt[c], st.acc[c].x + st.acc[c].y);
+        st.acc[c] = nx;
+        st.tgt[c] = (int)((ctl >> (8 + 8 * c)) & 255u);
+      }
+    }
+  }
 }
 
-// what a run still holds for class c after its last pair (the last segment's sum)
-FE_HD float fe_drain_leftover(const fe_drain_state& st, int c) { return (st.acc[c].x + st.acc[c].y) + st.pend[c]; }
+// what a half holds for class c after its last batch (run 0, half 1: plus bin n_fft/4 with power p_mid)
+FE_HD float fe_drain_leftover(const fe_drain_state& st, int c, float p_mid, float wmid) {
+  return fmaf(p_mid, wmid, st.acc[c].x + st.acc[c].y);
+}
+
+// Half 1 of a run, after its walk, with half 0's leftovers l0[class]: stores the segment that straddles the halves
+// (unless it is also the run's last one) and returns the run's leftovers in left[class].
+template <class Emit>
+FE_HD void fe_drain_join_halves(const fe_drain_state& st, const fe_drain_hdr& hdr, int run, const float* l0, float p_mid,
+                                float* left, Emit& emit) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    left[c] = fe_drain_leftover(st, c, p_mid, run == 0 ? hdr.wmid[c] : 0.0f);
+    if (hdr.open_tgt[run][c] != FE_DRAIN_NONE) {
+      if (hdr.open_last[run][c]) left[c] += l0[c];
+      else emit(hdr.open_tgt[run][c], st.defer[c] + l0[c]);
+    }
+  }
+}
 
 #endif  // FE_GEMM_CUH_

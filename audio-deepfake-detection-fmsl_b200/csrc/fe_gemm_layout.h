@@ -24,35 +24,46 @@
 
 // ---- drain tables ----------------------------------------------------------------------------------------
 // A drain thread owns one frame (TMEM lane) and one RUN of bins: GEMM column k carries bin k (run 0, ascending) and
-// bin n_fft/2 - k (run 1, descending); run 0 also takes bin n_fft/4 (evaluated by the producers) as column n_fft/4.
-// Both runs walk ALL columns 0 .. n_fft/4 - 1 in PAIRS (2p, 2p+1) with packed fp32x2 arithmetic (one issue slot for
-// two columns), then one more (virtual) pair for column n_fft/4.  Every bin may carry at most one even-indexed and
-// one odd-indexed filter (true for triangular banks), so a run needs two accumulators (class = filter parity), each
-// with an even-column half (.x) and an odd-column half (.y).  Along a run the filter of a class is piecewise
-// constant; a SEGMENT is a maximal range of columns with the same filter (or none).  The host packer normalises the
-// segments (short filter-less ranges are absorbed with zero weights) and requires every segment to span >= 3
-// columns; a filter then occupies exactly one segment of one class of a run (or the last segment of both runs when
-// it straddles bin n_fft/4), so the value a thread holds when a segment ends is the filter's FINAL energy for the
-// frame: it is stored straight to the workspace (no shared-memory scratch, no second pass).
-//   O switch at pair p: column 2p+1 is the first odd column of a new segment   -> pend = acc.y, acc.y = 0
-//   E switch at pair p: column 2p   is the first even column of a new segment  -> store acc.x + pend, acc.x = pend = 0,
-//                       the class is re-targeted at the new segment's filter
-// (O comes in the same pair as E or in the pair before it; switches are the same for all threads: table driven,
-// branch-uniform.)  After the last pair the two runs' leftovers are the straddling filters: run 1 hands its pair to
-// run 0 through shared memory where the targets coincide.
+// bin n_fft/2 - k (run 1, descending); run 0 also takes bin n_fft/4 (evaluated by the producers) after its last
+// column.  Both runs walk ALL columns 0 .. n_fft/4 - 1 in BATCHES of 8 columns = 4 pairs (2p, 2p+1), with packed
+// fp32x2 arithmetic (one issue slot for two columns).  Every bin may carry at most one even-indexed and one
+// odd-indexed filter (true for triangular banks), so a run needs one accumulator per filter parity (CLASS), with an
+// even-column half (.x) and an odd-column half (.y).  Along a run the filter of a class is piecewise constant; a
+// SEGMENT is a maximal range of columns with the same filter (or none; the host packer absorbs short filter-less
+// ranges with zero weights).  A filter occupies exactly one segment of one class of a run (or the last segment of
+// both runs when it straddles bin n_fft/4), so the sum a thread holds when a segment ends is the filter's FINAL
+// energy for the frame: it is stored straight to the workspace (no shared-memory scratch, no second pass).
+// Segment ends are handled per batch, outside the arithmetic: the packer requires at most one segment boundary per
+// class inside a batch window (k0, k0+8].  Weights `w` of a batch are those of the segment active at its first column
+// (zero behind the boundary); a batch with a boundary has its flag set and a second weight set `wn` for the columns
+// behind the boundary: the thread sums those into a fresh accumulator, stores the finished one and carries on with the
+// fresh one, aimed at the new filter.  Flags are the same for all threads: table driven, branch-uniform.
+// After the last batch the two runs' leftovers are the straddling filters: run 1 hands its pair to run 0 through
+// shared memory where the targets coincide.
 struct alignas(16) fe_drain_w {
   float w[2][2];     // [class = filter parity][half]: weights at columns (2p, 2p+1)
 };
-// control word of a pair: bits 0-1 class 0 (bit 0: O switch, bit 1: E switch), bits 2-3 class 1,
-// bits 8-15 / 16-23: filter the class is aimed at after its E switch (FE_DRAIN_NONE: no filter)
+// COLUMN HALVES.  The walk of a run is split between two threads: half 0 takes columns [0, n_fft/8), half 1 the
+// rest (and, for run 0, bin n_fft/4).  Per class at most one segment straddles column n_fft/8 ("open" segment): half 0
+// ends with its left part as leftover; half 1's first boundary of that class (control bit "defer") keeps the right
+// part in a register instead of storing it, and adds half 0's leftover (shared memory, one named barrier per tile)
+// before it stores; when half 1 has no boundary of the class at all, the open segment is also its last one and half
+// 0's leftover joins half 1's.
+// control word of a batch: bit 0 / 1: class 0 / 1 has a boundary in (k0, k0+8]; bit 2 / 3: that boundary's finished
+// segment is the open one (deferred); bits 8-15 / 16-23: filter the class is aimed at behind the boundary
+// (FE_DRAIN_NONE: no filter)
 #define FE_DRAIN_NONE 255
+#define FE_DRAIN_BATCH 8
 struct fe_drain_hdr {
-  int32_t first[2][2];   // [run][class] filter of the first segment (FE_DRAIN_NONE: none)
-  int32_t last[2][2];    // [run][class] filter of the last segment
-  int32_t merge[2];      // [class] 1: the last segments of the two runs are the same filter (run 0 stores the sum)
+  int32_t first[2][2][2];  // [run][half][class] filter of the half's first segment (FE_DRAIN_NONE: none)
+  int32_t last[2][2];      // [run][class] filter of the run's last segment
+  int32_t merge[2];        // [class] 1: the last segments of the two runs are the same filter (run 0 stores the sum)
+  int32_t open_tgt[2][2];  // [run][class] filter of the segment that straddles the halves (FE_DRAIN_NONE: no such segment)
+  int32_t open_last[2][2]; // [run][class] 1: half 1 has no boundary of the class: the open segment is the run's last one
+  float wmid[2];           // [class] weight of bin n_fft/4 (run 0, last segment)
   int32_t pad[2];
 };
-FE_HD int fe_drain_pairs_padded(int nhalf) { return ((nhalf / 2 + 1) + 3) & ~3; }   // pairs per run incl. the virtual one, x4
+// table sizes per run: w[nhalf/2] pairs, wn[nhalf/8][class 2][pair-in-batch 4] (fe_drain_w.w[class] slices), ctl[nhalf/8]
 
 // UMMA K-major, no-swizzle operand tile of `rows` rows x 16 K-values (one K=16 MMA step):
 // [K chunk of 8][row][8 halfs] -> descriptor LBO (K-chunk stride) = rows*16 B, SBO (8-row group) = 128 B.

@@ -26,7 +26,7 @@ gemm_geom geometry(const b200fe_params* p) {
   const int kpairs = p->win_length / 2;
   const int nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return g;
-  if (nhalf % 8 != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM
+  if (nhalf % 16 != 0 || nhalf < 32 || nhalf > 128) return g;  // 4 accumulators of nhalf columns fit TMEM; two halves of whole batches
   g.ok = true;
   g.kpairs = kpairs;
   g.nhalf = nhalf;
@@ -48,30 +48,33 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
   off = fe_align16(off + h->gemm_b_bytes);
   h->off_gemm_mid = (int32_t)off;
   off = fe_align16(off + (int64_t)2 * g.kpairs * 4);
-  const int pp = fe_drain_pairs_padded(g.nhalf);
   h->off_gemm_dw = (int32_t)off;
-  off = fe_align16(off + (int64_t)2 * pp * sizeof(fe_drain_w));
+  off = fe_align16(off + (int64_t)2 * (g.nhalf / 2) * sizeof(fe_drain_w));
   h->off_gemm_dctl = (int32_t)off;
-  off = fe_align16(off + (int64_t)2 * pp * 4);
+  off = fe_align16(off + (int64_t)2 * (g.nhalf / FE_DRAIN_BATCH) * 4);
   h->off_gemm_dids = (int32_t)off;
   off = fe_align16(off + (int64_t)sizeof(fe_drain_hdr));
+  h->off_gemm_dwn = (int32_t)off;
+  off = fe_align16(off + (int64_t)2 * (g.nhalf / FE_DRAIN_BATCH) * 16 * 4);
   h->gemm_ok = 1;  // provisional: fe_gemm_pack clears it when the window / filterbank do not qualify
   return off;
 }
 
-// Drain tables (fe_gemm_layout.h): per run and column pair the weights of the two filter-parity classes x two halves,
-// the switch codes and the filters the classes are aimed at.  Returns false when the filterbank does not qualify: a
-// bin with two filters of the same parity, a filter whose support along a run is not one range of >= 3 columns, or
-// a filter without any bin (its energy would never be stored).
+// Drain tables (fe_gemm_layout.h): per run the pair weights of the two filter-parity classes, per batch the boundary
+// flags, new targets and the weights behind the boundary.  Returns false when the filterbank does not qualify: a bin
+// with two filters of the same parity, a filter in two separate ranges of a run, two boundaries of one class in one
+// batch window, or a filter without any bin (its energy would never be stored).
 static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, int nhalf, char* base) {
-  if (nhalf % 8 != 0 || nfil > FE_GEMM_MAX_FILTERS || nfil >= FE_DRAIN_NONE) return false;
-  const int pp = fe_drain_pairs_padded(nhalf), npairs = nhalf / 2, nyq = 2 * nhalf;
+  if (nhalf % (2 * FE_DRAIN_BATCH) != 0 || nfil > FE_GEMM_MAX_FILTERS || nfil >= FE_DRAIN_NONE) return false;
+  const int npairs = nhalf / 2, nbatch = nhalf / FE_DRAIN_BATCH, nyq = 2 * nhalf;
   fe_drain_w* dw = (fe_drain_w*)(base + h->off_gemm_dw);
   uint32_t* dctl = (uint32_t*)(base + h->off_gemm_dctl);
   fe_drain_hdr* hdr = (fe_drain_hdr*)(base + h->off_gemm_dids);
-  memset(dw, 0, (size_t)2 * pp * sizeof(fe_drain_w));
-  memset(dctl, 0, (size_t)2 * pp * 4);
+  float* dwn = (float*)(base + h->off_gemm_dwn);
+  memset(dw, 0, (size_t)2 * npairs * sizeof(fe_drain_w));
+  memset(dctl, 0, (size_t)2 * nbatch * 4);
   memset(hdr, 0, sizeof(*hdr));
+  memset(dwn, 0, (size_t)2 * nbatch * 16 * 4);
   // filter of parity `par` with weight on `bin` (-1: none, -2: more than one)
   auto filter_of = [&](int bin, int par) {
     int f_found = -1;
@@ -80,53 +83,70 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
     return f_found;
   };
   std::vector<int> seen(nfil, 0);
-  const int ncol = nhalf + 2;   // columns 0 .. nhalf-1, column nhalf (bin n_fft/4: run 0 only) and one virtual odd column
   for (int run = 0; run < 2; ++run) {
     for (int par = 0; par < 2; ++par) {
+      // columns 0 .. nhalf-1, and for run 0 column nhalf = bin n_fft/4 (added by the thread after its last batch)
+      const int ncol = run == 0 ? nhalf + 1 : nhalf;
       std::vector<int> f(ncol, -1);
-      const int nreal = run == 0 ? nhalf + 1 : nhalf;
-      for (int k = 0; k < nreal; ++k) {
+      for (int k = 0; k < ncol; ++k) {
         f[k] = filter_of(run == 0 ? k : nyq - k, par);
         if (f[k] == -2) return false;
       }
-      // filter-less ranges shorter than 3 columns are absorbed by the following (else the preceding) segment
-      for (int k = 0; k < nreal;) {
+      // filter-less ranges shorter than a batch are absorbed by the following (else the preceding) segment, with zero
+      // weights: fewer boundaries
+      for (int k = 0; k < ncol;) {
         int e = k;
-        while (e + 1 < nreal && f[e + 1] == f[k]) ++e;
-        if (f[k] == -1 && e - k + 1 < 3) {
-          const int repl = e + 1 < nreal ? f[e + 1] : (k > 0 ? f[k - 1] : -1);
+        while (e + 1 < ncol && f[e + 1] == f[k]) ++e;
+        if (f[k] == -1 && e - k + 1 < FE_DRAIN_BATCH) {
+          const int repl = e + 1 < ncol ? f[e + 1] : (k > 0 ? f[k - 1] : -1);
           for (int i = k; i <= e; ++i) f[i] = repl;
         }
         k = e + 1;
       }
-      for (int k = nreal; k < ncol; ++k) f[k] = f[nreal - 1];   // virtual columns continue the last segment
-      // every segment >= 3 columns (the last one may be shorter only through its virtual columns), a filter in
-      // at most one segment of the class
+      // a filter in at most one segment of the class
       std::vector<int> seg_of(nfil, 0);
       for (int k = 0; k < ncol;) {
         int e = k;
         while (e + 1 < ncol && f[e + 1] == f[k]) ++e;
-        if (e - k + 1 < 3) return false;
         if (f[k] >= 0) {
           if (seg_of[f[k]]++) return false;
           seen[f[k]] |= 1 << run;
         }
         k = e + 1;
       }
-      hdr->first[run][par] = f[0] < 0 ? FE_DRAIN_NONE : f[0];
+      auto weight = [&](int k, int filt) { return filt < 0 ? 0.0f : fbank[(int64_t)(run == 0 ? k : nyq - k) * nfil + filt]; };
+      const int ksplit = nhalf / 2;   // first column of half 1
+      hdr->first[run][0][par] = f[0] < 0 ? FE_DRAIN_NONE : f[0];
+      hdr->first[run][1][par] = f[ksplit] < 0 ? FE_DRAIN_NONE : f[ksplit];
       hdr->last[run][par] = f[ncol - 1] < 0 ? FE_DRAIN_NONE : f[ncol - 1];
-      for (int p = 0; p <= npairs; ++p) {
-        fe_drain_w& w = dw[run * pp + p];
-        for (int hh = 0; hh < 2; ++hh) {
-          const int k = 2 * p + hh;
-          if (k < nreal && f[k] >= 0) w.w[par][hh] = fbank[(int64_t)(run == 0 ? k : nyq - k) * nfil + f[k]];
+      const bool open = f[ksplit] == f[ksplit - 1] && f[ksplit] >= 0;   // a filter's segment straddles the halves
+      hdr->open_tgt[run][par] = open ? f[ksplit] : FE_DRAIN_NONE;
+      bool open_pending = open;
+      if (run == 0) hdr->wmid[par] = weight(nhalf, f[nhalf]);
+      for (int b = 0; b < nbatch; ++b) {
+        const int k0 = b * FE_DRAIN_BATCH;
+        // boundaries in the window (k0, k0 + 8]: column c is a boundary when f[c] != f[c-1] (c = k0 + 8 may be the
+        // run's end: column nhalf of run 0, or nothing for run 1)
+        int bcol = -1;
+        for (int c = k0 + 1; c <= k0 + FE_DRAIN_BATCH && c < ncol; ++c)
+          if (f[c] != f[c - 1]) { if (bcol >= 0) return false; bcol = c; }
+        for (int i = 0; i < FE_DRAIN_BATCH; ++i) {
+          const int k = k0 + i;
+          const bool behind = bcol >= 0 && k >= bcol;
+          const float wv = weight(k, f[k]);
+          if (!behind) dw[run * npairs + k / 2].w[par][k & 1] = wv;
+          else dwn[((run * nbatch + b) * 2 + par) * 8 + i] = wv;   // [pair in batch][half] = column order
         }
-        uint32_t code = 0;
-        if (p > 0 && f[2 * p + 1] != f[2 * p - 1]) code |= 1u;   // O switch
-        if (p > 0 && f[2 * p] != f[2 * p - 2]) code |= 2u;       // E switch
-        const uint32_t tgt = f[2 * p] < 0 ? FE_DRAIN_NONE : (uint32_t)f[2 * p];
-        dctl[run * pp + p] |= (code << (2 * par)) | (tgt << (8 + 8 * par));
+        if (bcol >= 0) {
+          const uint32_t tgt = f[bcol] < 0 ? FE_DRAIN_NONE : (uint32_t)f[bcol];
+          dctl[run * nbatch + b] |= (1u << par) | (tgt << (8 + 8 * par));
+          if (k0 >= ksplit && open_pending) {   // half 1's first boundary ends the open segment
+            dctl[run * nbatch + b] |= 4u << par;
+            open_pending = false;
+          }
+        }
       }
+      hdr->open_last[run][par] = open_pending ? 1 : 0;
     }
   }
   for (int par = 0; par < 2; ++par) {
@@ -138,7 +158,6 @@ static bool pack_drain_tables(fe_blob_header* h, const float* fbank, int nfil, i
     if (seen[f] == 0) return false;
     if (seen[f] == 3 && !(hdr->merge[f & 1] && hdr->last[0][f & 1] == f)) return false;
   }
-  h->gemm_nbuf = 0;
   return true;
 }
 

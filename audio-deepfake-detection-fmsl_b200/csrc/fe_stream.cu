@@ -4,19 +4,22 @@
 // frames = the 128 TMEM lanes of one M=128 MMA, whatever utterances they belong to, so every tile is full.
 // One persistent CTA per SM walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...
 //
-// Warp roles (23 warps):
-//    0- 7  drain      warp = (TMEM lane quarter, run): tcgen05.ld of the four accumulators, packed fp32x2 powers of the
-//                     run's bins (run 0: bin k, run 1: bin n_fft/2 - k) and sliding even/odd triangular-filter sums
-//                     over column pairs (fe_gemm_layout.h).  A finished filter segment is the filter's final energy for
-//                     the frame and goes straight to the workspace [row][filter][frame]; the two runs meet once per
-//                     tile for the filters that straddle bin n_fft/4.  TMEM is released after the last tcgen05.ld.
-//    8-19  producers  three groups of four warps (lane = frame).  Per tile: max|x| per hop block -> per-frame
-//                     power-of-two scale, then production units u = 2*stage + K half (16 sample pairs of every frame:
-//                     fold + scale + fp16 hi/lo split into the UMMA A tiles), unit u by group u % 3.  The A slots are
-//                     not aliased by anything, so the first two stages of tile i+1 are produced while tile i is drained.
-//   20-21  MMA        one issuing thread per sub-GEMM pair (ce, co / se, so): per stage 3 x 2 tcgen05.mma (M=128,
+// Warp roles (27 warps):
+//    0-15  drain      warp = (TMEM lane quarter, run, column half): tcgen05.ld of the four accumulators, packed fp32x2
+//                     powers of the run's bins (run 0: bin k, run 1: bin n_fft/2 - k) and sliding even/odd
+//                     triangular-filter sums over column pairs (fe_gemm_layout.h).  A finished filter segment is the
+//                     filter's final energy for the frame and goes straight to the workspace [row][filter][frame]; the
+//                     four walkers of a frame meet once per tile for the segments that straddle the column halves and
+//                     bin n_fft/4.  TMEM is released after the last tcgen05.ld.  (A drain warp issues about one
+//                     instruction per five cycles -- dependent packed-FMA chains -- so the drain time is set by how
+//                     many warps share the walk, not by the issue slots: profiles/r2_stream_v3_*.)
+//   16-23  producers  two groups of four warps (lane = frame).  Per tile: max|x| per hop block -> per-frame
+//                     power-of-two scale, then production units (stage, K half): 16 sample pairs of every frame, fold +
+//                     scale + fp16 hi/lo split into the UMMA A tiles; group = K half.  The A slots are not aliased by
+//                     anything, so the first two stages of tile i+1 are produced while tile i is drained.
+//   24-25  MMA        one issuing thread per sub-GEMM pair (ce, co / se, so): per stage 3 x 2 tcgen05.mma (M=128,
 //                     N=n_fft/4, K=16: hi*hi + lo*hi + hi*lo) into the 4 TMEM accumulators, tcgen05.commit -> mbarriers
-//   22     loader     per tile: the hop blocks the tile's frames need, once each, as a handful of TMA tensor boxes
+//   26     loader     per tile: the hop blocks the tile's frames need, once each, as a handful of TMA tensor boxes
 //                     {32 floats, hop/32, 2^k hop blocks} with the 128-byte swizzle: hop blocks sit densely in shared
 //                     memory and lane <-> frame reads are still conflict-free.  A small 1-D bulk copy costs the TMA
 //                     unit ~90 cycles whatever its size, hence boxes.  Reflect-padded edge blocks are synthesised
@@ -33,9 +36,9 @@
 
 namespace {
 
-constexpr int kDrainWarps = 8;        // warps 0..7: quarter = warp & 3, run = warp >> 2
-constexpr int kProducerWarp0 = 8;
-constexpr int kProducerGroups = 3;    // (tests/emu/fe_emu.cpp mirrors the unit -> group mapping)
+constexpr int kDrainWarps = 16;       // warps 0..15: quarter = warp & 3, run = (warp >> 2) & 1, column half = warp >> 3
+constexpr int kProducerWarp0 = kDrainWarps;
+constexpr int kProducerGroups = 2;    // group = K half of the stage (tests/emu/fe_emu.cpp mirrors the unit -> group mapping)
 constexpr int kProducerWarps = 4 * kProducerGroups;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kMmaWarp0 = kProducerWarp0 + kProducerWarps;   // warps 20, 21: MMA issuers, two sub-GEMMs each (ce, co / se, so)
@@ -58,27 +61,30 @@ struct stream_args {
   int32_t total_frames, tile_frames, n_tiles, top_db_group;
 };
 
+constexpr int kNumBars = 12;   // BAR_COUNT below
+
 struct smem_layout {
-  int samp, a_stage, b_stage, dw, dctl, dhdr, mid, gmax, us2, midp, exch, bars, tmem_slot, total;
+  int samp, a_stage, b_stage, dw, dwn, dctl, dhdr, mid, gmax, us2, midp, exl0, exch, bars, tmem_slot, total;
 };
 
 __host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpairs) {
   smem_layout L;
-  const int pp = fe_drain_pairs_padded(nhalf);
   int off = 0;
   L.samp = off;      off += kMaxSlots * hop * 4;            // dense hop-block rows, 128-byte swizzled (base 1024-aligned)
   off = (off + 127) & ~127;
   L.a_stage = off;   off += 2 * kAStageBytes;
   L.b_stage = off;   off += 2 * fe_gemm_b_stage_bytes(nhalf);
-  L.dw = off;        off += 2 * pp * (int)sizeof(fe_drain_w);
-  L.dctl = off;      off += 2 * pp * 4;
+  L.dw = off;        off += 2 * (nhalf / 2) * (int)sizeof(fe_drain_w);
+  L.dwn = off;       off += 2 * (nhalf / FE_DRAIN_BATCH) * 16 * 4;
+  L.dctl = off;      off += (2 * (nhalf / FE_DRAIN_BATCH) * 4 + 15) & ~15;
   L.dhdr = off;      off += (int)sizeof(fe_drain_hdr);
   L.mid = off;       off += kpairs * 4;          // interleaved weights of bin n_fft/4: even j -> Re, odd j -> Im
   L.gmax = off;      off += ((kMaxSlots + 1) * 4 + 15) & ~15;   // max |x| per hop block of the tile
   L.us2 = off;       off += 2 * kTileM * 4;                       // [tile parity][frame] unscale^2
   L.midp = off;      off += 2 * kProducerGroups * kTileM * 8;     // [tile parity][producer group][frame] (Re, Im) partials of bin n_fft/4
+  L.exl0 = off;      off += 2 * 2 * 2 * kTileM * 4;               // [tile parity][run][class][frame] half 0 -> half 1 leftovers
   L.exch = off;      off += 2 * 2 * kTileM * 4;                   // [tile parity][class][frame] run 1 -> run 0 straddler partials
-  L.bars = off;      off += 16 * 8;
+  L.bars = off;      off += kNumBars * 8;
   L.tmem_slot = off; off += 16;
   L.total = off;
   return L;
@@ -86,6 +92,7 @@ __host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpair
 
 enum { BAR_SAMP_FULL = 0, BAR_SAMP_EMPTY = 1, BAR_A_FULL = 2, BAR_B_FULL = 4, BAR_STAGE_FREE = 6, BAR_ACC_FULL = 8,
        BAR_ACC_EMPTY = 9, BAR_PROD_DONE = 10, BAR_COUNT = 12 };
+static_assert(BAR_COUNT == kNumBars, "barrier count");
 
 #ifdef FE_GEMM_TRACE
 #define ST_TRACE(ev, it, q) do { if (blockIdx.x == 0 && (it) < 8) { ((long long*)(a.error_flag + 64))[((it) * 8 + (q)) * 16 + (ev)] = clock64(); } } while (0)
@@ -105,6 +112,11 @@ __device__ __forceinline__ void tma_box_4d(uint32_t dst, const CUtensorMap* map,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 // max |x| of every hop block of a tile, by `nwarps` warps (this one is `w`): 8 lanes per row, 4 rows per pass (a row
@@ -133,23 +145,70 @@ __device__ __forceinline__ void scout_rows(const unsigned char* s_samp, float* s
 }
 
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory"); }
-__device__ __forceinline__ void quarter_bar(int quarter) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory"); }
+__device__ __forceinline__ void quarter_bar(int quarter) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory"); }   // the frame quarter's four walkers
+__device__ __forceinline__ void runs_bar(int quarter) { asm volatile("bar.sync %0, 64;" ::"r"(6 + quarter) : "memory"); }      // its two half-1 walkers
 
-// a finished filter segment of the drain: final energy of (frame, filter) -> workspace
+// a finished filter segment of the drain: final energy of (frame, filter) -> workspace (32-bit element offsets: a
+// launch's energies are < 2^31 bytes, fe_stream_supported)
 struct emit_store {
-  float* dst;        // energies + (row * n_filter) * n_frames + t
-  size_t n_frames;
+  float* base;        // energies of the launch
+  uint32_t off;       // (row * n_filter) * n_frames + t
+  uint32_t n_frames;
   int n_filter;
   bool valid;
   float us2, vmax;
   __device__ __forceinline__ void operator()(int f, float v) {
     if (valid && f < n_filter) {
       const float e = v * us2;
-      dst[(size_t)f * n_frames] = e;
+      base[off + (uint32_t)f * n_frames] = e;
       vmax = fmaxf(vmax, e);
     }
   }
 };
+
+// The walk of one drain thread over its columns [k_begin, k_end) (fe_gemm_layout.h).  The last batch releases the
+// thread's share of TMEM right after its tcgen05.ld has landed.
+template <int RUN>
+__device__ __forceinline__ void drain_walk(uint32_t taddr, int nhalf, int k_begin, int k_end, const fe_drain_w* w_run,
+                                           const uint32_t* ctl_run, const float* wn_run, fe_drain_state& st, emit_store& emit,
+                                           uint32_t acc_empty_bar, int lane) {
+  const uint32_t t1 = taddr + (uint32_t)nhalf, t2 = t1 + (uint32_t)nhalf, t3 = t2 + (uint32_t)nhalf;
+#pragma unroll 1
+  for (int k0 = k_begin; k0 < k_end; k0 += 8) {
+    float ce[8], co[8], se[8], so[8];
+#ifdef FE_EXP_NO_LDTM   // timing experiment: arithmetic without the tensor-memory loads
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ce[i] = emit.us2 + i; co[i] = emit.us2 * i; se[i] = emit.us2 - i; so[i] = emit.us2 * 0.5f * i; }
+#else
+    tmem_ld8(taddr + (uint32_t)k0, ce);
+    tmem_ld8(t1 + (uint32_t)k0, co);
+    tmem_ld8(t2 + (uint32_t)k0, se);
+    tmem_ld8(t3 + (uint32_t)k0, so);
+#endif
+    const unsigned ctl = ctl_run[k0 >> 3];
+    fe_drain_w w[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) w[p] = w_run[(k0 >> 1) + p];
+    tmem_ld_wait();
+    tmem_ld_tie8(ce); tmem_ld_tie8(co); tmem_ld_tie8(se); tmem_ld_tie8(so);
+    if (k0 + 8 >= k_end) {
+      // this walker's share of the accumulators is in registers: TMEM is free for the next tile's MMAs once all 16 say so
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty_bar);
+    }
+    fe_f2 pw[4];
+#ifdef FE_EXP_NO_MATH   // timing experiment: the tensor-memory loads without the arithmetic
+    st.acc[0].x += ce[0] + co[1] + se[2] + so[3];
+    continue;
+#endif
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      pw[p] = fe_drain_power<RUN>(fe_f2{ce[2 * p], ce[2 * p + 1]}, fe_f2{co[2 * p], co[2 * p + 1]}, fe_f2{se[2 * p], se[2 * p + 1]},
+                                  fe_f2{so[2 * p], so[2 * p + 1]});
+    fe_drain_batch(pw, w, wn_run + (k0 >> 3) * 16, ctl, st, emit);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_constant__ tmaps8 maps, const stream_args a) {
@@ -160,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
   const int nF = a.n_frames, hop = a.hop, nfil = a.n_filter;
   const int rs = hop * 4;        // bytes per hop-block row (dense; the 128-byte swizzle keeps lane <-> frame reads conflict-free)
-  const int pp = fe_drain_pairs_padded(a.nhalf);
+  const int npairs = a.nhalf / 2, nbatch = a.nhalf / FE_DRAIN_BATCH;
 
   if (!h->gemm_ok) {
     // tables without the variant's tiles (a C-ABI caller that set variant = DFT_GEMM without asking
@@ -172,11 +231,13 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   unsigned char* s_samp = smem + L.samp;
   fe_drain_w* s_dw = reinterpret_cast<fe_drain_w*>(smem + L.dw);
   uint32_t* s_dctl = reinterpret_cast<uint32_t*>(smem + L.dctl);
+  float* s_dwn = reinterpret_cast<float*>(smem + L.dwn);
   fe_drain_hdr* s_dhdr = reinterpret_cast<fe_drain_hdr*>(smem + L.dhdr);
   float* s_mid = reinterpret_cast<float*>(smem + L.mid);
   float* s_gmax = reinterpret_cast<float*>(smem + L.gmax);
   float* s_us2 = reinterpret_cast<float*>(smem + L.us2);
   float2* s_midp = reinterpret_cast<float2*>(smem + L.midp);
+  float* s_exl0 = reinterpret_cast<float*>(smem + L.exl0);
   float* s_exch = reinterpret_cast<float*>(smem + L.exch);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const uint32_t bars = smem_u32(smem + L.bars);
@@ -185,9 +246,11 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   // ---- one-time setup -----------------------------------------------------------------------------
   {
     const fe_drain_w* gdw = reinterpret_cast<const fe_drain_w*>(blob + h->off_gemm_dw);
-    for (int i = tid; i < 2 * pp; i += kThreads) s_dw[i] = gdw[i];
+    for (int i = tid; i < 2 * npairs; i += kThreads) s_dw[i] = gdw[i];
     const uint32_t* gctl = reinterpret_cast<const uint32_t*>(blob + h->off_gemm_dctl);
-    for (int i = tid; i < 2 * pp; i += kThreads) s_dctl[i] = gctl[i];
+    for (int i = tid; i < 2 * nbatch; i += kThreads) s_dctl[i] = gctl[i];
+    const float* gwn = reinterpret_cast<const float*>(blob + h->off_gemm_dwn);
+    for (int i = tid; i < 2 * nbatch * 16; i += kThreads) s_dwn[i] = gwn[i];
     const int32_t* ghdr = reinterpret_cast<const int32_t*>(blob + h->off_gemm_dids);
     for (int i = tid; i < (int)(sizeof(fe_drain_hdr) / 4); i += kThreads) reinterpret_cast<int32_t*>(s_dhdr)[i] = ghdr[i];
     const float* gmid = reinterpret_cast<const float*>(blob + h->off_gemm_mid);
@@ -277,6 +340,20 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) ST_TRACE(9, it, 0);
       if (lane == 0) mbar_arrive(bar(BAR_SAMP_FULL));
+      // the next tile's ordinary hop blocks -> L2 now, so that its boxes (issued once the producers release the sample
+      // buffer) do not wait for HBM
+      if (tile + (int)gridDim.x < a.n_tiles) {
+        const fe_tile_geo gn = fe_tile_geometry(tile + gridDim.x, a.tile_frames, a.total_frames, nF);
+        for (int row = gn.row0; row <= gn.row_last; ++row) {
+          const int v_lo = max(gn.sv0 - row * (nF + 1), 1), v_hi = min(gn.sv0 + gn.nv - 1 - row * (nF + 1), nF - 1);
+          const int cnt = v_hi - v_lo + 1;
+          if (cnt <= 0) continue;
+          if (lane < 8 && ((cnt >> lane) & 1)) {
+            const int first = cnt & ~((2 << lane) - 1);
+            tma_prefetch_4d(&maps.m[lane], 0, 0, v_lo - 1 + first, row);
+          }
+        }
+      }
       if (lane == 0) {
         for (int q = 0; q < a.nstages; ++q, ++n) {
           const uint32_t s = n & 1u, par = (n >> 1) & 1u;
@@ -337,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
   } else if (warp >= kProducerWarp0) {
     // ================================ producers (warps 8..19) =========================================
     const int pw = warp - kProducerWarp0;
-    const int grp = pw >> 2;               // production units u with u % 3 == grp
+    const int grp = pw >> 2;               // production units (stage, K half = grp)
     const int quarter = pw & 3;
     const int m = quarter * 32 + lane;
     uint32_t n0 = 0, it = 0;
@@ -358,8 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       const uint32_t brow = (uint32_t)(slot * rs), frow = brow + (uint32_t)rs;   // byte offsets into the sample buffer
       float mid_re = 0.0f, mid_im = 0.0f;
 #pragma unroll 1
-      for (int u = grp; u < 2 * a.nstages; u += kProducerGroups) {
-        const int q = u >> 1, khalf = u & 1;
+      for (int q = 0; q < a.nstages; ++q) {
+        const int khalf = grp;
         const uint32_t n = n0 + (uint32_t)q, s = n & 1u, par = (n >> 1) & 1u;
         const int j0 = 32 * q + 16 * khalf;
         float fwd[16], bwd[16], buf[16];
@@ -385,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_A_FULL + s));
-        if (lane == 0 && quarter == 0) ST_TRACE(2, it, u >> 1);
+        if (lane == 0 && quarter == 0) ST_TRACE(2, it, q);
       }
       // each group files its own partial of bin n_fft/4 (fixed unit -> group mapping: the sum does not depend on the tile)
       s_midp[(tp * kProducerGroups + grp) * kTileM + m] = make_float2(mid_re, mid_im);
@@ -396,13 +473,16 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       }
     }
   } else {
-    // ================================ drain (warps 0..7) ==============================================
+    // ================================ drain (warps 0..15) =============================================
     const int quarter = warp & 3;          // TMEM lane quarter
-    const int run = warp >> 2;             // 0: bins k (ascending) + bin n_fft/4, 1: bins n_fft/2 - k
+    const int run = (warp >> 2) & 1;       // 0: bins k (ascending) + bin n_fft/4, 1: bins n_fft/2 - k
+    const int half = warp >> 3;            // columns [half * n_fft/8, (half + 1) * n_fft/8)
     const int m = quarter * 32 + lane;
-    const fe_drain_w* w_run = s_dw + run * pp;
-    const uint32_t* ctl_run = s_dctl + run * pp;
+    const fe_drain_w* w_run = s_dw + run * npairs;
+    const uint32_t* ctl_run = s_dctl + run * nbatch;
+    const float* wn_run = s_dwn + run * nbatch * 16;
     const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int k_begin = half * (a.nhalf >> 1), k_end = k_begin + (a.nhalf >> 1);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
@@ -413,73 +493,48 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       // the producers' per-frame values of this tile (scale, bin n_fft/4 partials)
       mbar_wait(bar(BAR_PROD_DONE + tp), (it >> 1) & 1u, a.error_flag, 9);
       emit_store emit;
-      emit.dst = a.energies + (size_t)row * nfil * nF + t;
-      emit.n_frames = (size_t)nF;
+      emit.base = a.energies;
+      emit.off = (uint32_t)((row * nfil) * nF + t);
+      emit.n_frames = (uint32_t)nF;
       emit.n_filter = nfil;
       emit.valid = m < g.count;
       emit.us2 = s_us2[tp * kTileM + m];
       emit.vmax = 0.0f;
       float p_mid = 0.0f;
-      if (run == 0) {
-        const float2 v0 = s_midp[(tp * kProducerGroups + 0) * kTileM + m], v1 = s_midp[(tp * kProducerGroups + 1) * kTileM + m],
-                     v2 = s_midp[(tp * kProducerGroups + 2) * kTileM + m];
+      if (run == 0 && half == 1) {
+        const float2 v0 = s_midp[(tp * kProducerGroups + 0) * kTileM + m], v1 = s_midp[(tp * kProducerGroups + 1) * kTileM + m];
         const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);   // scaled sample units -> accumulator units
-        const float re = ((v0.x + v1.x) + v2.x) * bs, im = ((v0.y + v1.y) + v2.y) * bs;
+        const float re = (v0.x + v1.x) * bs, im = (v0.y + v1.y) * bs;
         p_mid = fmaf(re, re, im * im);
       }
       fe_drain_state st;
-      fe_drain_init(st, *s_dhdr, run);
+      fe_drain_init(st, *s_dhdr, run, half);
       mbar_wait(bar(BAR_ACC_FULL), tp, a.error_flag, 8);
       tc_fence_after();
-      if (lane == 0 && quarter == 0) ST_TRACE(4, it, run);
-#pragma unroll 1
-      for (int k0 = 0; k0 < a.nhalf; k0 += 8) {
-        float ce[8], co[8], se[8], so[8];
-        tmem_ld8(tbase + (uint32_t)(0 * a.nhalf + k0), ce);
-        tmem_ld8(tbase + (uint32_t)(1 * a.nhalf + k0), co);
-        tmem_ld8(tbase + (uint32_t)(2 * a.nhalf + k0), se);
-        tmem_ld8(tbase + (uint32_t)(3 * a.nhalf + k0), so);
-        const uint4 ctl = *reinterpret_cast<const uint4*>(ctl_run + (k0 >> 1));
-        const fe_drain_w w0 = w_run[(k0 >> 1) + 0], w1 = w_run[(k0 >> 1) + 1], w2 = w_run[(k0 >> 1) + 2], w3 = w_run[(k0 >> 1) + 3];
-        tmem_ld_wait();
-        tmem_ld_tie8(ce); tmem_ld_tie8(co); tmem_ld_tie8(se); tmem_ld_tie8(so);
-        if (k0 + 8 >= a.nhalf) {
-          // the tile's accumulators are in registers: TMEM is free for the next tile's MMAs
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY));
-        }
-        if (run == 0) {
-          fe_drain_pair<0>(fe_f2{ce[0], ce[1]}, fe_f2{co[0], co[1]}, fe_f2{se[0], se[1]}, fe_f2{so[0], so[1]}, w0, ctl.x, st, emit);
-          fe_drain_pair<0>(fe_f2{ce[2], ce[3]}, fe_f2{co[2], co[3]}, fe_f2{se[2], se[3]}, fe_f2{so[2], so[3]}, w1, ctl.y, st, emit);
-          fe_drain_pair<0>(fe_f2{ce[4], ce[5]}, fe_f2{co[4], co[5]}, fe_f2{se[4], se[5]}, fe_f2{so[4], so[5]}, w2, ctl.z, st, emit);
-          fe_drain_pair<0>(fe_f2{ce[6], ce[7]}, fe_f2{co[6], co[7]}, fe_f2{se[6], se[7]}, fe_f2{so[6], so[7]}, w3, ctl.w, st, emit);
-        } else {
-          fe_drain_pair<1>(fe_f2{ce[0], ce[1]}, fe_f2{co[0], co[1]}, fe_f2{se[0], se[1]}, fe_f2{so[0], so[1]}, w0, ctl.x, st, emit);
-          fe_drain_pair<1>(fe_f2{ce[2], ce[3]}, fe_f2{co[2], co[3]}, fe_f2{se[2], se[3]}, fe_f2{so[2], so[3]}, w1, ctl.y, st, emit);
-          fe_drain_pair<1>(fe_f2{ce[4], ce[5]}, fe_f2{co[4], co[5]}, fe_f2{se[4], se[5]}, fe_f2{so[4], so[5]}, w2, ctl.z, st, emit);
-          fe_drain_pair<1>(fe_f2{ce[6], ce[7]}, fe_f2{co[6], co[7]}, fe_f2{se[6], se[7]}, fe_f2{so[6], so[7]}, w3, ctl.w, st, emit);
-        }
-      }
-      if (lane == 0 && quarter == 0) ST_TRACE(5, it, run);
-      // the virtual pair of column n_fft/4 (run 0: the producers' bin), then the runs' leftovers = straddling filters
-      fe_drain_last_pair(p_mid, w_run[a.nhalf >> 1], ctl_run[a.nhalf >> 1], st, emit);
-      float* ex = s_exch + tp * 2 * kTileM + m;
-      if (run == 1) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float v = fe_drain_leftover(st, c);
-          if (s_dhdr->merge[c]) ex[c * kTileM] = v;
-          else emit(s_dhdr->last[1][c], v);
-        }
+      if (lane == 0 && quarter == 0) ST_TRACE(4, it, warp >> 2);
+      if (run == 0) drain_walk<0>(tbase, a.nhalf, k_begin, k_end, w_run, ctl_run, wn_run, st, emit, bar(BAR_ACC_EMPTY), lane);
+      else drain_walk<1>(tbase, a.nhalf, k_begin, k_end, w_run, ctl_run, wn_run, st, emit, bar(BAR_ACC_EMPTY), lane);
+      if (lane == 0 && quarter == 0) ST_TRACE(5, it, warp >> 2);
+      // the segments that straddle the column halves, then the runs' leftovers = the filters that straddle bin n_fft/4
+      float* l0p = s_exl0 + ((tp * 2 + run) * 2) * kTileM + m;   // [class] stride kTileM
+      if (half == 0) {
+        l0p[0] = fe_drain_leftover(st, 0, 0.0f, 0.0f);
+        l0p[kTileM] = fe_drain_leftover(st, 1, 0.0f, 0.0f);
         quarter_bar(quarter);
       } else {
         quarter_bar(quarter);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v = fe_drain_leftover(st, c);
-          if (s_dhdr->merge[c]) v += ex[c * kTileM];
-          emit(s_dhdr->last[0][c], v);
+        const float l0[2] = {l0p[0], l0p[kTileM]};
+        float left[2];
+        fe_drain_join_halves(st, *s_dhdr, run, l0, p_mid, left, emit);
+        float* ex = s_exch + tp * 2 * kTileM + m;
+        if (run == 1) {
+          if (s_dhdr->merge[0]) ex[0] = left[0]; else emit(s_dhdr->last[1][0], left[0]);
+          if (s_dhdr->merge[1]) ex[kTileM] = left[1]; else emit(s_dhdr->last[1][1], left[1]);
+          runs_bar(quarter);
+        } else {
+          runs_bar(quarter);
+          emit(s_dhdr->last[0][0], s_dhdr->merge[0] ? left[0] + ex[0] : left[0]);
+          emit(s_dhdr->last[0][1], s_dhdr->merge[1] ? left[1] + ex[kTileM] : left[1]);
         }
       }
       if (a.group_max) {
@@ -493,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           atomicMax(a.group_max + grp_id, __float_as_uint(emit.vmax));
         }
       }
-      if (lane == 0 && quarter == 0) ST_TRACE(6, it, run);
+      if (lane == 0 && quarter == 0) ST_TRACE(6, it, warp >> 2);
     }
   }
 
@@ -533,7 +588,7 @@ bool fe_gemm_supported(const b200fe_params* p) {
   if (p->win_length != 2 * p->hop_length || p->win_length > p->n_fft) return false;
   const int kpairs = p->win_length / 2, nhalf = p->n_fft / 4;
   if (kpairs % 32 != 0 || kpairs < 32 || kpairs > 256) return false;
-  if (nhalf % 8 != 0 || nhalf < 32 || nhalf > 128) return false;   // 4 accumulators fit TMEM
+  if (nhalf % 16 != 0 || nhalf < 32 || nhalf > 128) return false;   // 4 accumulators fit TMEM; two column halves of whole batches
   return make_layout(p->hop_length, nhalf, kpairs).total <= 227 * 1024;
 }
 
@@ -554,7 +609,7 @@ int64_t fe_gemm_workspace_bytes(const b200fe_params* p, int64_t chunk_rows, int6
 bool fe_stream_supported(const b200fe_params* p, int64_t T, int64_t rows) {
   if (!fe_gemm_supported(p)) return false;
   const int64_t nF = 1 + T / p->hop_length;
-  if (nF < 2 || rows * nF >= (int64_t)1 << 30) return false;
+  if (nF < 2 || rows * nF >= (int64_t)1 << 30 || rows * nF * p->n_filter >= (int64_t)1 << 31) return false;   // 32-bit element offsets
   if (T <= p->n_fft / 2 || (T & 3) != 0) return false;
   return true;
 }

@@ -139,10 +139,10 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
   if (h->magic != FE_BLOB_MAGIC || !h->gemm_ok) return -1;
   const int T = (int)T_, hop = p->hop_length, nF = 1 + T / hop, nfil = p->n_filter;
   const int kpairs = h->gemm_kpairs, nhalf = h->gemm_nhalf, nstages = kpairs / 32;
-  const int pp = fe_drain_pairs_padded(h->gemm_nhalf);
   const fe_drain_w* dw = (const fe_drain_w*)(blob + h->off_gemm_dw);
   const uint32_t* dctl = (const uint32_t*)(blob + h->off_gemm_dctl);
   const fe_drain_hdr* hdr = (const fe_drain_hdr*)(blob + h->off_gemm_dids);
+  const float* dwn = (const float*)(blob + h->off_gemm_dwn);
   const float* gmid = (const float*)(blob + h->off_gemm_mid);
   const unsigned char* gB = blob + h->off_gemm_b;
   const int M = FE_GEMM_TILE_M;
@@ -153,7 +153,7 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
   const int n_tiles = (total + tf - 1) / tf;
   std::vector<unsigned char> a_stage(fe_gemm_a_stage_bytes());
   std::vector<float> D((size_t)4 * M * nhalf);
-  const int kProducerGroups = 3;   // fe_stream.cu: production unit u = 2*stage + khalf belongs to warp group u % 3
+  const int kProducerGroups = 2;   // fe_stream.cu: production unit (stage, khalf) belongs to warp group khalf
   std::vector<float> samp, bmax;
   for (int tile = 0; tile < n_tiles; ++tile) {
     const fe_tile_geo g = fe_tile_geometry(tile, tf, total, nF);
@@ -194,7 +194,7 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
           bwd[0] = (j0 == 0) ? fwd[0] : brow[hop - j0];
           for (int i = 1; i < 16; ++i) bwd[i] = brow[hop - j0 - i];
           fe_u4 chunk[8];
-          const int grp = (2 * q + khalf) % kProducerGroups;   // each group accumulates its own partial of bin n_fft/4
+          const int grp = khalf;   // each group accumulates its own partial of bin n_fft/4
           fe_stream_produce_unit(fwd, bwd, scale[m], midc.data() + j0, mre[(size_t)grp * M + m], mim[(size_t)grp * M + m], chunk);
           for (int sf = 0; sf < 8; ++sf)
             memcpy(a_stage.data() + sf * fe_gemm_tile_bytes(M) + fe_gemm_operand_offset(M, m, 8 * khalf), &chunk[sf], 16);
@@ -224,27 +224,37 @@ extern "C" int fe_emu_gemm_energies(const float* wave, int64_t R, int64_t T_, co
         if (f < nfil) energies[((size_t)row * nfil + f) * nF + t] = v * us2;
       };
       float left[2][2];
+      const int nbatch = nhalf / FE_DRAIN_BATCH, npairs = nhalf / 2;
       for (int run = 0; run < 2; ++run) {
-        fe_drain_state st;
-        fe_drain_init(st, *hdr, run);
-        for (int p = 0; p < nhalf / 2; ++p) {
-          const int k = 2 * p;
-          const fe_f2 c0 = fe_f2{D[((size_t)0 * M + m) * nhalf + k], D[((size_t)0 * M + m) * nhalf + k + 1]};
-          const fe_f2 c1 = fe_f2{D[((size_t)1 * M + m) * nhalf + k], D[((size_t)1 * M + m) * nhalf + k + 1]};
-          const fe_f2 s0 = fe_f2{D[((size_t)2 * M + m) * nhalf + k], D[((size_t)2 * M + m) * nhalf + k + 1]};
-          const fe_f2 s1 = fe_f2{D[((size_t)3 * M + m) * nhalf + k], D[((size_t)3 * M + m) * nhalf + k + 1]};
-          if (run == 0) fe_drain_pair<0>(c0, c1, s0, s1, dw[p], dctl[p], st, emit);
-          else fe_drain_pair<1>(c0, c1, s0, s1, dw[pp + p], dctl[pp + p], st, emit);
+        float l0[2] = {0.0f, 0.0f};
+        for (int half = 0; half < 2; ++half) {
+          fe_drain_state st;
+          fe_drain_init(st, *hdr, run, half);
+          for (int b = half * nbatch / 2; b < (half + 1) * nbatch / 2; ++b) {
+            fe_f2 pw[4];
+            for (int p = 0; p < 4; ++p) {
+              const int k = b * FE_DRAIN_BATCH + 2 * p;
+              const fe_f2 c0 = fe_f2{D[((size_t)0 * M + m) * nhalf + k], D[((size_t)0 * M + m) * nhalf + k + 1]};
+              const fe_f2 c1 = fe_f2{D[((size_t)1 * M + m) * nhalf + k], D[((size_t)1 * M + m) * nhalf + k + 1]};
+              const fe_f2 s0 = fe_f2{D[((size_t)2 * M + m) * nhalf + k], D[((size_t)2 * M + m) * nhalf + k + 1]};
+              const fe_f2 s1 = fe_f2{D[((size_t)3 * M + m) * nhalf + k], D[((size_t)3 * M + m) * nhalf + k + 1]};
+              pw[p] = run == 0 ? fe_drain_power<0>(c0, c1, s0, s1) : fe_drain_power<1>(c0, c1, s0, s1);
+            }
+            fe_drain_batch(pw, dw + run * npairs + b * 4, dwn + (size_t)(run * nbatch + b) * 16, dctl[run * nbatch + b], st, emit);
+          }
+          if (half == 0) {
+            for (int c = 0; c < 2; ++c) l0[c] = fe_drain_leftover(st, c, 0.0f, 0.0f);
+          } else {
+            float p_mid = 0.0f;
+            if (run == 0) {
+              const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
+              const float re = (mre[m] + mre[(size_t)M + m]) * bs;
+              const float im = (mim[m] + mim[(size_t)M + m]) * bs;
+              p_mid = fmaf(re, re, im * im);
+            }
+            fe_drain_join_halves(st, *hdr, run, l0, p_mid, left[run], emit);
+          }
         }
-        float p_mid = 0.0f;
-        if (run == 0) {
-          const float bs = (float)(1 << FE_GEMM_B_SCALE_LOG2);
-          const float re = ((mre[m] + mre[(size_t)M + m]) + mre[(size_t)2 * M + m]) * bs;
-          const float im = ((mim[m] + mim[(size_t)M + m]) + mim[(size_t)2 * M + m]) * bs;
-          p_mid = fmaf(re, re, im * im);
-        }
-        fe_drain_last_pair(p_mid, dw[run * pp + nhalf / 2], dctl[run * pp + nhalf / 2], st, emit);
-        for (int c = 0; c < 2; ++c) left[run][c] = fe_drain_leftover(st, c);
       }
       for (int c = 0; c < 2; ++c) {
         if (hdr->merge[c]) {
