@@ -13,7 +13,7 @@ from . import _lib
 from .transforms import (ComputeDeltas, FrontEndEngine, LFCC, LFCCDelta, MelSpectrogram, Spectrogram,
                          create_dct, linear_fbanks, melscale_fbanks)
 from .maze import LFCC_FILTS, FeatureSlot, MazeScorer, fill_deterministic
-from .evaluation import eer_min_dcf, gather_scores, shard_range, write_score_file
+from .evaluation import eer_min_dcf, eer_min_dcf_device, gather_scores, shard_range, write_score_file
 
 # names SURVEY.md 8(b) uses for the drop-in modules
 B200LFCC = LFCC
@@ -27,5 +27,5 @@ __all__ = [
     "B200LFCC", "B200LFCCDelta", "B200MelSpectrogram", "B200Spectrogram", "B200ComputeDeltas",
     "linear_fbanks", "melscale_fbanks", "create_dct",
     "MazeScorer", "FeatureSlot", "LFCC_FILTS", "fill_deterministic",
-    "shard_range", "gather_scores", "eer_min_dcf", "write_score_file",
+    "shard_range", "gather_scores", "eer_min_dcf", "eer_min_dcf_device", "write_score_file",
 ]

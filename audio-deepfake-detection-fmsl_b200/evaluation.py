@@ -69,6 +69,40 @@ def eer_min_dcf(y_true, y_score) -> Tuple[float, float, float]:
     return float(fpr[i]), float(np.min(fnr + fpr)), float(thr[i])
 
 
+def eer_min_dcf_device(y_true: torch.Tensor, y_score: torch.Tensor, *, sync: bool = True):
+    """The same three numbers computed ON THE DEVICE by ``b200fe_eer_min_dcf`` (one CUDA kernel: stable radix sort
+    by decreasing score, distinct-score points, scikit-learn's ``drop_intermediate`` pruning, float64 rates —
+    Maze5_eval.py:588-594), from scores that never left the GPU (SURVEY 8f-2).  ``y_true``: labels, 1 = bonafide;
+    ``y_score``: float32 CUDA tensor.  With ``sync=False`` returns the float64[4] device tensor
+    ``(eer, min_dcf, threshold, status)`` without synchronising; otherwise ``(eer, min_dcf, threshold)`` as floats
+    (raises ``ValueError`` when only one class is present, like the host version)."""
+    from . import _lib
+    import ctypes as C
+    if y_score.device.type != "cuda" or y_score.dtype != torch.float32 or y_score.dim() != 1:
+        raise TypeError("eer_min_dcf_device expects a 1-D float32 CUDA tensor of scores (no CPU fallback: use eer_min_dcf)")
+    n = y_score.numel()
+    if y_true.numel() != n or n < 1:
+        raise ValueError("labels and scores must have the same, non-zero length")
+    dev = y_score.device
+    scores = y_score.contiguous()
+    labels = y_true.to(device=dev, dtype=torch.int32).contiguous()
+    lib = _lib.load()
+    ws_bytes = _lib.check(lib.b200fe_eer_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(4, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.b200fe_eer_min_dcf(scores.data_ptr(), labels.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                          C.c_void_p(stream)))
+    ws.record_stream(torch.cuda.current_stream(dev))
+    if not sync:
+        return out
+    eer, dcf, thr, status = out.tolist()
+    if status != 0.0:
+        raise ValueError("EER needs both classes present (Maze5_eval.py:577-582 returns {} in that case)")
+    return eer, dcf, thr
+
+
 def write_score_file(path: str, utt_ids, scores) -> None:
     """``"<utt_id> <score>\\n"`` per line — the wire format the reference's analysis tools read
     (produce_evaluation_file, maze5.py:415-430)."""

@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor, nn
 
-from .evaluation import eer_min_dcf, gather_scores, shard_range
+from .evaluation import eer_min_dcf, eer_min_dcf_device, gather_scores, shard_range
 
 N_BONAFIDE, N_SPOOF = 7355, 63882          # Eval.py:58-60
 N_EVAL = N_BONAFIDE + N_SPOOF              # 71,237
@@ -96,11 +96,24 @@ def run_sweep(frontend: nn.Module, scorer: nn.Module, device: torch.device, *, n
     g1.record()
     torch.cuda.synchronize(device)
     gather_ms = g0.elapsed_time(g1)
+    # ROC / EER / min-DCF on the device, from the gathered scores where they are (b200fe_eer_min_dcf); the labels are
+    # a function of the utterance index
+    y_dev = (torch.arange(n_total, device=device) < n_bonafide).to(torch.int32)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    metrics_dev = eer_min_dcf_device(y_dev, full.contiguous(), sync=False)
+    e1.record()
+    eer, dcf, thr, status = metrics_dev.tolist()           # the sweep's only device -> host read of results: 32 bytes
+    if status != 0.0:
+        raise ValueError("EER needs both classes present")
+    eer_ms = e0.elapsed_time(e1)
+    wall = time.perf_counter() - t0
+    # (kept for the record and the tests: the host restatement of the reference's sklearn call on the same scores)
     scores = full.cpu().numpy()
     checks = gather_scores(local_ck, n_total, group).cpu().numpy()
-    wall = time.perf_counter() - t0
-    eer, dcf, thr = eer_min_dcf(labels(n_total, n_bonafide), scores)
-    return dict(n_total=n_total, n_local=hi - lo, eer=eer, min_dcf=dcf, eer_threshold=thr,
+    host = eer_min_dcf(labels(n_total, n_bonafide), scores)
+    return dict(n_total=n_total, n_local=hi - lo, eer=eer, min_dcf=dcf, eer_threshold=thr, eer_device_ms=eer_ms,
+                eer_host=host[0], min_dcf_host=host[1], eer_threshold_host=host[2],
                 scores_sha256=hashlib.sha256(scores.astype("<f4").tobytes()).hexdigest(),
                 features_sha256=hashlib.sha256(checks.astype("<i8").tobytes()).hexdigest(),
                 frontend_ms=fe_ms, classifier_ms=cls_ms, gather_ms=gather_ms, wall_s=wall, scores=scores)

@@ -262,6 +262,8 @@ def config4_record(frontend, dev, rank, world):
             "classifier_ms": cls_ms, "frontend_plus_classifier_utt_per_s": r["n_total"] / ((fe_ms + cls_ms) * 1e-3),
             "score_gather_us": g_ms * 1e3, "score_gather": "one all_gather_into_tensor of float32[ceil(N/W)] per rank (NCCL)" if world > 1 else "single rank: no collective",
             "wall_ms": wall_ms, "eer": r["eer"], "min_dcf": r["min_dcf"], "eer_threshold": r["eer_threshold"],
+            "eer_on_device_us": 1e3 * r["eer_device_ms"], "eer_equals_host_sklearn_restatement": bool(
+                (r["eer"], r["min_dcf"], r["eer_threshold"]) == (r["eer_host"], r["min_dcf_host"], r["eer_threshold_host"])),
             "features_sha256": r["features_sha256"],
             "timing": "CUDA events per batch summed per rank, max over ranks; gather timed alone with CUDA events"}
 

@@ -188,6 +188,21 @@ int32_t b200fe_features_forward_host_i16(const int16_t* pcm_host, int64_t R, int
                                          size_t staging_bytes, int64_t chunk_rows, void* const* streams,
                                          int32_t n_streams);
 
+/* ---- scoring tail on the device ---------------------------------------------------
+ * Replaces the host-side  fpr, tpr, thr = sklearn.metrics.roc_curve(y, s); fnr = 1 - tpr;
+ * eer = fpr[nanargmin |fnr - fpr|]; min_dcf = min(fnr + fpr)  of Thesis/02_Evaluation_Scripts/Maze5_eval.py:588-594
+ * (also score_file_processor.py:176-196), with roc_curve's default drop_intermediate=True: the same three numbers,
+ * digit for digit, computed in float64 from scores that never left the device.
+ *   scores  float32 device [n]   per-utterance scores (maze5.py:425: log-softmax column 1)
+ *   labels  int32 device [n]     1 = bonafide (positive class), anything else = spoof
+ *   out4    float64 device [4]   eer, min_dcf, eer threshold, status (0 ok, 1 = only one class present: the
+ *                                reference returns no metrics then, Maze5_eval.py:577-582)
+ *   workspace  device scratch >= b200fe_eer_workspace_bytes(n), 16-byte aligned
+ * One kernel on `stream`; no synchronisation (the caller reads out4 when it needs the numbers). */
+int64_t b200fe_eer_workspace_bytes(int64_t n);
+int32_t b200fe_eer_min_dcf(const float* scores, const int32_t* labels, int64_t n, double* out4, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* Number of kernel launches the last b200fe_*_forward call on this thread enqueued (bench.py's
  * gpu_launches figure is counted from this). */
 int64_t b200fe_last_launch_count(void);

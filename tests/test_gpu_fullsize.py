@@ -227,3 +227,50 @@ def test_pcm16_host_path_is_bit_identical_to_float_path(fe):
     assert out_i.shape == (300, 60, 404)
     assert torch.equal(out_i, out_f)
     assert torch.equal(out_i, m(torch.from_numpy(xf).to(dev())).cpu())
+
+
+def _sk_metrics(y, s):
+    from sklearn.metrics import roc_curve
+    fpr, tpr, thr = roc_curve(y, s)
+    fnr = 1 - tpr
+    i = int(np.nanargmin(np.absolute(fnr - fpr)))
+    return float(fpr[i]), float(np.min(fnr + fpr)), float(thr[i])
+
+
+@pytest.mark.parametrize("n,decimals", [(71237, None), (71237, 2), (7123, 1), (1000, 0), (3, None), (2, None), (40000, 3)])
+def test_device_eer_equals_sklearn_digit_for_digit(fe, n, decimals):
+    """b200fe_eer_min_dcf against sklearn.metrics.roc_curve + the reference's formulas
+    (Maze5_eval.py:588-594): the same float64 numbers, with heavy score ties (rounded scores), negative zeros,
+    tiny inputs and the sweep's own size."""
+    rs = np.random.RandomState(n + (decimals or 7))
+    y = (rs.rand(n) < 0.103).astype(np.int64)
+    y[0], y[-1] = 1, 0
+    s = (rs.randn(n) + 1.1 * y).astype(np.float32)
+    if decimals is not None:
+        s = np.round(s, decimals).astype(np.float32)
+        s[s == 0] = np.where(rs.rand(int((s == 0).sum())) < 0.5, np.float32(-0.0), np.float32(0.0))
+    want = _sk_metrics(y, s)
+    got = fe.eer_min_dcf_device(torch.from_numpy(y).to(dev()), torch.from_numpy(s).to(dev()))
+    assert got == want, (n, decimals, got, want)
+    assert got == fe.eer_min_dcf(y, s)
+    # a perfect separation and a single-class input
+    yy = np.r_[np.ones(5), np.zeros(9)].astype(np.int64)
+    ss = np.r_[np.full(5, 2.0), np.linspace(-1, 1, 9)].astype(np.float32)
+    assert fe.eer_min_dcf_device(torch.from_numpy(yy).to(dev()), torch.from_numpy(ss).to(dev())) == _sk_metrics(yy, ss)
+    with pytest.raises(ValueError):
+        fe.eer_min_dcf_device(torch.ones(10, dtype=torch.int64, device=dev()), torch.randn(10, device=dev()))
+    with pytest.raises(TypeError):
+        fe.eer_min_dcf_device(torch.ones(10, dtype=torch.int64), torch.randn(10))
+
+
+def test_device_eer_in_the_sweep_equals_the_host_restatement(fe):
+    """The config-4 sweep takes its EER / min-DCF / threshold from the device kernel; the host restatement of the
+    reference's sklearn call on the same gathered scores must give the same numbers."""
+    from importlib import import_module
+    sweep = import_module("audio-deepfake-detection-fmsl_b200.sweep")
+    scorer = fe.MazeScorer(fe.LFCC_FILTS, fmsl=False)
+    fe.fill_deterministic(scorer, sweep.SEED)
+    scorer.to(dev())
+    r = sweep.run_sweep(fe.LFCCDelta(**LFCC_CFG), scorer, dev(), n_total=3000, n_bonafide=310, batch=512)
+    assert (r["eer"], r["min_dcf"], r["eer_threshold"]) == (r["eer_host"], r["min_dcf_host"], r["eer_threshold_host"])
+    assert _sk_metrics(sweep.labels(3000, 310), r["scores"]) == (r["eer"], r["min_dcf"], r["eer_threshold"])
