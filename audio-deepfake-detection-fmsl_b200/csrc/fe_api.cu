@@ -14,7 +14,19 @@ namespace {
 
 thread_local int64_t g_launches = 0;
 
-constexpr int64_t kWsTargetBytes = 48ll << 20;  // energies of one chunk stay well inside the 126 MB L2
+// Energies of one chunk of rows (the workspace between the energies kernel and the tail).  Round 1 kept a chunk inside
+// the 126 MB L2 (48 MB); measured on B200 the launch ramps and tails of three small launches cost more than the extra
+// 64 KB per utterance of DRAM traffic when the energies spill (the path runs at a quarter of the HBM roofline):
+// 48 MB 4.11 M utt/s, 96 MB 4.26 M, >= 140 MB (one chunk for 4096 rows) 4.40 M (profiles/r2_chunk_size_sweep.txt).
+// B200FE_WS_MB overrides the target (measurement hook).
+int64_t ws_target_bytes() {
+  static const int64_t v = [] {
+    const char* e = getenv("B200FE_WS_MB");
+    const long mb = e ? atol(e) : 0;
+    return (int64_t)(mb >= 1 && mb <= 4096 ? mb : 160) << 20;
+  }();
+  return v;
+}
 
 int32_t cuda_fail(cudaError_t e, const char* what) {
   fe_set_error("%s: %s", what, cudaGetErrorString(e));
@@ -51,7 +63,7 @@ int64_t group_max_bytes(const b200fe_params* p, int64_t R) {
 int64_t chunk_rows_for(const b200fe_params* p, int64_t R, int64_t n_frames) {
   if (needs_group_max(p) && p->top_db_group > 1) return R;  // maxima span rows: finish all rows first
   const int64_t per_row = (int64_t)p->n_filter * n_frames * 4;
-  int64_t c = kWsTargetBytes / (per_row > 0 ? per_row : 1);
+  int64_t c = ws_target_bytes() / (per_row > 0 ? per_row : 1);
   if (c < 148) c = 148;
   return c < R ? c : R;
 }

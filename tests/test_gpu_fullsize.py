@@ -3,7 +3,7 @@ torchaudio executed live on the host, and the measured distance of both fp32 imp
 evaluation on the tonal set S2 (written to gpurun_out/ so that the numbers, not only pass/fail, are kept).
 
   config 2   4096 S1 utterances, LFCC+delta+delta-delta, both kernel families        <= 1e-4
-  config 3   8192 S1 utterances, 80-band mel (14 workspace chunks), log = db/log/None  <= 1e-4
+  config 3   8192 S1 utterances, 80-band mel (several workspace chunks), log = db/log/None  <= 1e-4
   config 4   the whole 71,237-utterance sweep: torchaudio features on the host -> the same classifier ->
              EER / min-DCF equal to the CUDA sweep's, scores within 1e-4
 """
