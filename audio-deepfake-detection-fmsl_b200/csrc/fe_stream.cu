@@ -27,6 +27,8 @@
 // TMEM holds exactly the four accumulators (4 x 128 columns), so the MMAs of a tile and its drain cannot overlap;
 // the tile period is MMA phase + drain, everything else (sample loads, scout, production, stores) runs beside them.
 #include <atomic>
+#include <stdio.h>
+#include <unistd.h>
 
 #include "fe_tc.cuh"
 
@@ -46,8 +48,9 @@ constexpr int kNumMmaWarps = 2;
 constexpr int kLoaderWarp = kMmaWarp0 + kNumMmaWarps;
 constexpr int kThreads = (kLoaderWarp + 1) * 32;
 constexpr int kTileM = FE_GEMM_TILE_M;
-constexpr int kMaxSlots = 132;                    // hop blocks of a tile: 128 + 1 + one more per utterance boundary
+constexpr int kMaxSlots = 131;                    // hop blocks of a tile: 128 + 1 + one more per utterance boundary (at most two: fe_tile_frames)
 constexpr int kAStageBytes = 8 * 2 * kTileM * 16; // 32 KB: [sub 4][hi, lo] tiles of 128 rows x 16 K
+constexpr int kGmaxStride = (((kMaxSlots + 1) * 4 + 15) & ~15) / 4;   // floats per tile parity of the block maxima
 
 struct stream_args {
   const float* wave;        // first row of the launch
@@ -61,7 +64,7 @@ struct stream_args {
   int32_t total_frames, tile_frames, n_tiles, top_db_group;
 };
 
-constexpr int kNumBars = 12;   // BAR_COUNT below
+constexpr int kNumBars = 14;   // BAR_COUNT below
 
 struct smem_layout {
   int samp, a_stage, b_stage, dw, dwn, dctl, dhdr, mid, gmax, us2, midp, exl0, exch, bars, tmem_slot, total;
@@ -79,7 +82,7 @@ __host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpair
   L.dctl = off;      off += (2 * (nhalf / FE_DRAIN_BATCH) * 4 + 15) & ~15;
   L.dhdr = off;      off += (int)sizeof(fe_drain_hdr);
   L.mid = off;       off += kpairs * 4;          // interleaved weights of bin n_fft/4: even j -> Re, odd j -> Im
-  L.gmax = off;      off += ((kMaxSlots + 1) * 4 + 15) & ~15;   // max |x| per hop block of the tile
+  L.gmax = off;      off += 2 * (((kMaxSlots + 1) * 4 + 15) & ~15);   // [tile parity] max |x| per hop block of the tile
   L.us2 = off;       off += 2 * kTileM * 4;                       // [tile parity][frame] unscale^2
   L.midp = off;      off += 2 * kProducerGroups * kTileM * 8;     // [tile parity][producer group][frame] (Re, Im) partials of bin n_fft/4
   L.exl0 = off;      off += 2 * 2 * 2 * kTileM * 4;               // [tile parity][run][class][frame] half 0 -> half 1 leftovers
@@ -91,11 +94,17 @@ __host__ __device__ inline smem_layout make_layout(int hop, int nhalf, int kpair
 }
 
 enum { BAR_SAMP_FULL = 0, BAR_SAMP_EMPTY = 1, BAR_A_FULL = 2, BAR_B_FULL = 4, BAR_STAGE_FREE = 6, BAR_ACC_FULL = 8,
-       BAR_ACC_EMPTY = 9, BAR_PROD_DONE = 10, BAR_COUNT = 12 };
+       BAR_ACC_EMPTY = 9, BAR_PROD_DONE = 10, BAR_SCOUT_FULL = 12, BAR_COUNT = 14 };
 static_assert(BAR_COUNT == kNumBars, "barrier count");
 
 #ifdef FE_GEMM_TRACE
-#define ST_TRACE(ev, it, q) do { if (blockIdx.x == 0 && (it) < 8) { ((long long*)(a.error_flag + 64))[((it) * 8 + (q)) * 16 + (ev)] = clock64(); } } while (0)
+#ifndef FE_TRACE_CTA
+#define FE_TRACE_CTA 0
+#endif
+#ifndef FE_TRACE_IT0
+#define FE_TRACE_IT0 0
+#endif
+#define ST_TRACE(ev, it, q) do { if (blockIdx.x == FE_TRACE_CTA && (int)(it) >= FE_TRACE_IT0 && (int)(it) < FE_TRACE_IT0 + 8) { ((long long*)(a.error_flag + 64))[(((int)(it) - FE_TRACE_IT0) * 8 + (q)) * 16 + (ev)] = clock64(); } } while (0)
 #else
 #define ST_TRACE(ev, it, q) do { } while (0)
 #endif
@@ -119,32 +128,51 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
                : "memory");
 }
 
-// max |x| of every hop block of a tile, by `nwarps` warps (this one is `w`): 8 lanes per row, 4 rows per pass (a row
-// is a whole number of 128-byte lines, so the swizzle only permutes inside it)
-__device__ __forceinline__ void scout_rows(const unsigned char* s_samp, float* s_gmax, int rs, int nv, int w, int nwarps, int lane) {
-  const int c4 = rs / 16;                 // 16-byte chunks per row
+// max |x| of every hop block of a tile, straight from global memory, by `nwarps` warps (this one is `w`): 8 lanes per
+// hop block, 4 blocks per pass, every lane's loads of a pass in flight together.  The drain warps run this one tile
+// AHEAD of the sample loads, in the time they would otherwise idle behind the tile's MMAs: the per-frame scales are
+// known before the samples land in shared memory (nothing of it is on the producers' path), and the tile's hop blocks
+// are in L2 when the loader's TMA boxes ask for them.  Edge blocks (v = 0, v = nF: reflect padding) take the same
+// element-wise path the loader uses, so the maxima are those of exactly the samples the producers will see.
+__device__ __forceinline__ void scout_tile_global(const float* wave, int64_t T64, int nF, int hop, const fe_tile_geo& g,
+                                                  float* s_gmax, int w, int nwarps, int lane) {
+  const int T = (int)T64;
   const int r_in = lane >> 3, l8 = lane & 7;
-  for (int r0 = 4 * w; r0 < nv; r0 += 4 * nwarps) {
+  const int c4 = hop >> 2;                // 16-byte chunks per hop block (hop % 32 == 0: at most 64, 8 per lane)
+  for (int r0 = 4 * w; r0 < g.nv; r0 += 4 * nwarps) {
     const int r = r0 + r_in;
-    const float4* p = reinterpret_cast<const float4*>(s_samp + r * rs);
-    float4 v[8];                          // rs/16 <= 64 chunks per row: at most 8 per lane, all in flight together
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = l8 + 8 * u;
-      v[u] = (i < c4 && r < nv) ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     float mx = 0.0f;
+    if (r < g.nv) {
+      const int sv = g.sv0 + r;
+      const int row = sv / (nF + 1), v = sv - row * (nF + 1);
+      const float* x = wave + (int64_t)row * T64;
+      if (v > 0 && v < nF) {
+        const float4* p = reinterpret_cast<const float4*>(x + (int64_t)(v - 1) * hop);
+        float4 q[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+        for (int u = 0; u < 8; ++u) {
+          const int i = l8 + 8 * u;
+          q[u] = i < c4 ? __ldg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q[u].x), fabsf(q[u].y)), fmaxf(fabsf(q[u].z), fabsf(q[u].w))));
+      } else {
+        for (int e = l8; e < hop; e += 8) {
+          int idx = (v - 1) * hop + e;
+          idx = idx < 0 ? -idx : idx;
+          idx = idx >= T ? 2 * (T - 1) - idx : idx;
+          mx = fmaxf(mx, fabsf(__ldg(x + idx)));
+        }
+      }
+    }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-    if (l8 == 0 && r < nv) s_gmax[r] = mx;
+    if (l8 == 0 && r < g.nv) s_gmax[r] = mx;
   }
 }
 
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory"); }
 __device__ __forceinline__ void quarter_bar(int quarter) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory"); }   // the frame quarter's four walkers
 __device__ __forceinline__ void runs_bar(int quarter) { asm volatile("bar.sync %0, 64;" ::"r"(6 + quarter) : "memory"); }      // its two half-1 walkers
 
@@ -172,26 +200,37 @@ template <int RUN>
 __device__ __forceinline__ void drain_walk(uint32_t taddr, int nhalf, int k_begin, int k_end, const fe_drain_w* w_run,
                                            const uint32_t* ctl_run, const float* wn_run, fe_drain_state& st, emit_store& emit,
                                            uint32_t acc_empty_bar, int lane) {
-  const uint32_t t1 = taddr + (uint32_t)nhalf, t2 = t1 + (uint32_t)nhalf, t3 = t2 + (uint32_t)nhalf;
+  // running addresses (registers): four accumulator columns in tensor memory, the batch's tables in shared memory
+  uint32_t t0 = taddr + (uint32_t)k_begin;
+  const uint32_t tn = (uint32_t)nhalf;
+  uint32_t w_addr = smem_u32(w_run + (k_begin >> 1));
+  uint32_t ctl_addr = smem_u32(ctl_run + (k_begin >> 3));
+  uint32_t wn_addr = smem_u32(wn_run + (k_begin >> 3) * 16);
+  int left = (k_end - k_begin) >> 3;
 #pragma unroll 1
-  for (int k0 = k_begin; k0 < k_end; k0 += 8) {
+  for (; left > 0; --left, t0 += 8, w_addr += 64, ctl_addr += 4, wn_addr += 64) {
     float ce[8], co[8], se[8], so[8];
 #ifdef FE_EXP_NO_LDTM   // timing experiment: arithmetic without the tensor-memory loads
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ce[i] = emit.us2 + i; co[i] = emit.us2 * i; se[i] = emit.us2 - i; so[i] = emit.us2 * 0.5f * i; }
 #else
-    tmem_ld8(taddr + (uint32_t)k0, ce);
-    tmem_ld8(t1 + (uint32_t)k0, co);
-    tmem_ld8(t2 + (uint32_t)k0, se);
-    tmem_ld8(t3 + (uint32_t)k0, so);
+    tmem_ld8(t0, ce);
+    tmem_ld8(t0 + tn, co);
+    tmem_ld8(t0 + 2 * tn, se);
+    tmem_ld8(t0 + 3 * tn, so);
 #endif
-    const unsigned ctl = ctl_run[k0 >> 3];
-    fe_drain_w w[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) w[p] = w_run[(k0 >> 1) + p];
     tmem_ld_wait();
     tmem_ld_tie8(ce); tmem_ld_tie8(co); tmem_ld_tie8(se); tmem_ld_tie8(so);
-    if (k0 + 8 >= k_end) {
+    // the tables are fetched behind the wait (volatile: not hoisted above it): 16 fewer registers live across the
+    // tensor-memory loads, and the other walkers of the scheduler cover the shared-memory latency
+    unsigned ctl;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ctl) : "r"(ctl_addr));
+    fe_drain_w w[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[p].w[0][0]), "=f"(w[p].w[0][1]), "=f"(w[p].w[1][0]), "=f"(w[p].w[1][1])
+                   : "r"(w_addr + 16u * p));
+    if (left == 1) {
       // this walker's share of the accumulators is in registers: TMEM is free for the next tile's MMAs once all 16 say so
       tc_fence_before();
       __syncwarp();
@@ -206,8 +245,42 @@ __device__ __forceinline__ void drain_walk(uint32_t taddr, int nhalf, int k_begi
     for (int p = 0; p < 4; ++p)
       pw[p] = fe_drain_power<RUN>(fe_f2{ce[2 * p], ce[2 * p + 1]}, fe_f2{co[2 * p], co[2 * p + 1]}, fe_f2{se[2 * p], se[2 * p + 1]},
                                   fe_f2{so[2 * p], so[2 * p + 1]});
-    fe_drain_batch(pw, w, wn_run + (k0 >> 3) * 16, ctl, st, emit);
+    fe_drain_batch(pw, w, reinterpret_cast<const float*>(__cvta_shared_to_generic(wn_addr)), ctl, st, emit);
   }
+}
+
+// One production unit (stage q, K half): 16 sample pairs of frame m from the sample buffer (brow / frow: byte offsets of
+// the frame's backward / forward hop block), folded, scaled and split into the UMMA A tiles of slot `a_slot` (shared
+// address of the slot), then the slot's A_FULL arrival.
+
+__device__ __forceinline__ void produce_unit(const unsigned char* s_samp, uint32_t brow, uint32_t frow, int hop, int q, int khalf,
+                                             int m, float scale, const float* s_mid, float& mid_re, float& mid_im,
+                                             unsigned char* a_slot, uint32_t bar_stage_free, uint32_t free_parity,
+                                             uint32_t bar_a_full, int* error_flag, int lane) {
+  const int j0 = 32 * q + 16 * khalf;
+  float fwd[16], bwd[16], buf[16];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const float4 f = *reinterpret_cast<const float4*>(s_samp + swz(frow + j0 * 4 + ch * 16));
+    fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
+    float4 b;   // asm: keeps the 16-byte load whole even where only three of its elements are used
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "r"(smem_u32(s_samp) + swz(brow + (hop - j0 - 16) * 4 + ch * 16)));
+    buf[4 * ch + 0] = b.x; buf[4 * ch + 1] = b.y; buf[4 * ch + 2] = b.z; buf[4 * ch + 3] = b.w;
+  }
+  // bwd[i] = x[c - j0 - i] = backward-row element hop - j0 - i; element hop (i = 0, j0 = 0) is the centre sample
+  bwd[0] = (j0 == 0) ? fwd[0] : *reinterpret_cast<const float*>(s_samp + swz(brow + (hop - j0) * 4));
+#pragma unroll
+  for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
+  fe_u4 chunk[8];
+  fe_stream_produce_unit(fwd, bwd, scale, s_mid + j0, mid_re, mid_im, chunk);
+  mbar_wait(bar_stage_free, free_parity, error_flag, 7);   // MMAs of this slot's previous use retired
+  unsigned char* a_row = a_slot + khalf * kTileM * 16 + m * 16;
+#pragma unroll
+  for (int sf = 0; sf < 8; ++sf) *reinterpret_cast<fe_u4*>(a_row + sf * fe_gemm_tile_bytes(kTileM)) = chunk[sf];
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar_a_full);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -273,6 +346,8 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
     mbar_init(bar(BAR_ACC_EMPTY), kDrainWarps);
     mbar_init(bar(BAR_PROD_DONE + 0), kProducerWarps);
     mbar_init(bar(BAR_PROD_DONE + 1), kProducerWarps);
+    mbar_init(bar(BAR_SCOUT_FULL + 0), kDrainWarps);
+    mbar_init(bar(BAR_SCOUT_FULL + 1), kDrainWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp0) {
@@ -424,44 +499,23 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       const int row = (g.g0 + mm) / nF;
       const int slot = mm + (row - g.row0);               // backward hop block; the forward one is slot + 1
       const uint32_t tp = it & 1u;
+      // the drain warps have scouted this tile's hop blocks (max |x| each) one tile ahead, from global memory
+      mbar_wait(bar(BAR_SCOUT_FULL + tp), (it >> 1) & 1u, a.error_flag, 10);
+      float scale, unscale;
+      {
+        const float* gm = s_gmax + tp * kGmaxStride;
+        fe_gemm_frame_scale(2.0f * fmaxf(gm[slot], gm[slot + 1]), scale, unscale);
+      }
       mbar_wait(bar(BAR_SAMP_FULL), tp, a.error_flag, 6);
       if (tid == kProducerWarp0 * 32) ST_TRACE(1, it, 0);
-      scout_rows(s_samp, s_gmax, rs, g.nv, pw, kProducerWarps, lane);
-      producer_bar();
-      if (tid == kProducerWarp0 * 32) ST_TRACE(7, it, 0);
-      float scale, unscale;
-      fe_gemm_frame_scale(2.0f * fmaxf(s_gmax[slot], s_gmax[slot + 1]), scale, unscale);
       if (grp == 0) s_us2[tp * kTileM + m] = unscale * unscale;
       const uint32_t brow = (uint32_t)(slot * rs), frow = brow + (uint32_t)rs;   // byte offsets into the sample buffer
       float mid_re = 0.0f, mid_im = 0.0f;
 #pragma unroll 1
       for (int q = 0; q < a.nstages; ++q) {
-        const int khalf = grp;
-        const uint32_t n = n0 + (uint32_t)q, s = n & 1u, par = (n >> 1) & 1u;
-        const int j0 = 32 * q + 16 * khalf;
-        float fwd[16], bwd[16], buf[16];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const float4 f = *reinterpret_cast<const float4*>(s_samp + swz(frow + j0 * 4 + ch * 16));
-          fwd[4 * ch + 0] = f.x; fwd[4 * ch + 1] = f.y; fwd[4 * ch + 2] = f.z; fwd[4 * ch + 3] = f.w;
-          float4 b;   // asm: keeps the 16-byte load whole even where only three of its elements are used
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                       : "r"(smem_u32(s_samp) + swz(brow + (hop - j0 - 16) * 4 + ch * 16)));
-          buf[4 * ch + 0] = b.x; buf[4 * ch + 1] = b.y; buf[4 * ch + 2] = b.z; buf[4 * ch + 3] = b.w;
-        }
-        // bwd[i] = x[c - j0 - i] = backward-row element hop - j0 - i; element hop (i = 0, j0 = 0) is the centre sample
-        bwd[0] = (j0 == 0) ? fwd[0] : *reinterpret_cast<const float*>(s_samp + swz(brow + (hop - j0) * 4));
-#pragma unroll
-        for (int i = 1; i < 16; ++i) bwd[i] = buf[16 - i];
-        fe_u4 chunk[8];
-        fe_stream_produce_unit(fwd, bwd, scale, s_mid + j0, mid_re, mid_im, chunk);
-        mbar_wait(bar(BAR_STAGE_FREE + s), par ^ 1u, a.error_flag, 7);   // MMAs of this slot's previous use retired
-        unsigned char* a_row = smem + L.a_stage + s * kAStageBytes + khalf * kTileM * 16 + m * 16;
-#pragma unroll
-        for (int sf = 0; sf < 8; ++sf) *reinterpret_cast<fe_u4*>(a_row + sf * fe_gemm_tile_bytes(kTileM)) = chunk[sf];
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_A_FULL + s));
+        const uint32_t n = n0 + (uint32_t)q, sl = n & 1u, par = (n >> 1) & 1u;
+        produce_unit(s_samp, brow, frow, hop, q, grp, m, scale, s_mid, mid_re, mid_im, smem + L.a_stage + sl * kAStageBytes,
+                     bar(BAR_STAGE_FREE + sl), par ^ 1u, bar(BAR_A_FULL + sl), a.error_flag, lane);
         if (lane == 0 && quarter == 0) ST_TRACE(2, it, q);
       }
       // each group files its own partial of bin n_fft/4 (fixed unit -> group mapping: the sum does not depend on the tile)
@@ -483,6 +537,16 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
     const float* wn_run = s_dwn + run * nbatch * 16;
     const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int k_begin = half * (a.nhalf >> 1), k_end = k_begin + (a.nhalf >> 1);
+    // block maxima of this CTA's first two tiles (afterwards: tile i + 2 behind the drain of tile i)
+    for (int pre = 0; pre < 2; ++pre) {
+      const int tile = blockIdx.x + pre * gridDim.x;
+      if (tile < a.n_tiles) {
+        const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
+        scout_tile_global(a.wave, a.T, nF, hop, g, s_gmax + pre * kGmaxStride, warp, kDrainWarps, lane);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL + pre));
+    }
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
       const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
@@ -549,6 +613,18 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         }
       }
       if (lane == 0 && quarter == 0) ST_TRACE(6, it, warp >> 2);
+      // the block maxima two tiles ahead (the producers finished reading this parity's maxima long before this tile's
+      // MMAs ended)
+      {
+        const int tile2 = tile + 2 * (int)gridDim.x;
+        if (tile2 < a.n_tiles) {
+          const fe_tile_geo g2 = fe_tile_geometry(tile2, a.tile_frames, a.total_frames, nF);
+          scout_tile_global(a.wave, a.T, nF, hop, g2, s_gmax + tp * kGmaxStride, warp, kDrainWarps, lane);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL + tp));
+        if (lane == 0 && quarter == 0) ST_TRACE(7, it, warp >> 2);
+      }
     }
   }
 
@@ -581,6 +657,9 @@ encode_tiled_fn get_encode() {
 
 }  // namespace
 
+#ifdef FE_GEMM_TRACE
+int* fe_trace_host_flag = nullptr;
+#endif
 int32_t fe_gemm_compiled(void) { return 1; }
 
 bool fe_gemm_supported(const b200fe_params* p) {
@@ -691,12 +770,42 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
   const int sms = fe_device_sms(dev);
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
 #ifdef FE_GEMM_TRACE
+  {   // debug build: a host-mapped copy of the timeout flag, printed by the process at exit
+    static int* host_flag = nullptr;
+    extern int* fe_trace_host_flag;
+    if (!host_flag) {
+      cudaHostAlloc((void**)&host_flag, 64, cudaHostAllocMapped);
+      host_flag[0] = 0;
+      int* dptr = nullptr;
+      cudaHostGetDevicePointer((void**)&dptr, host_flag, 0);
+      cudaMemcpyToSymbol(g_fe_host_flag, &dptr, sizeof(dptr));
+      fe_trace_host_flag = host_flag;
+      static struct printer { int* p; ~printer() { fprintf(stderr, "fe_stream timeout flag (code*1000+warp): %d\n", p[0]); } } pr{host_flag};
+    }
+  }
   cudaError_t e = cudaMemsetAsync(a.error_flag, 0, 65536, stream);
 #else
   cudaError_t e = cudaMemsetAsync(a.error_flag, 0, 4, stream);
 #endif
   if (e != cudaSuccess) return e;
   fe_stream_kernel<<<grid, kThreads, smem, stream>>>(*maps_p, a);
+#ifdef FE_GEMM_TRACE
+  {   // debug build: report a protocol timeout as soon as the kernel flags it (the launch may never return afterwards)
+    int* hf = nullptr;
+    cudaMemcpyFromSymbol(&hf, g_fe_host_flag, sizeof(hf));
+    (void)hf;
+    extern int* fe_trace_host_flag;
+    for (int spin = 0; spin < 20000; ++spin) {
+      if (fe_trace_host_flag && fe_trace_host_flag[0]) {
+        fprintf(stderr, "fe_stream timeout flag (code*1000+warp): %d\n", fe_trace_host_flag[0]);
+        fflush(stderr);
+        _exit(3);
+      }
+      if (cudaStreamQuery(stream) != cudaErrorNotReady) break;
+      usleep(1000);
+    }
+  }
+#endif
   *launches = 1;
   return cudaGetLastError();
 }

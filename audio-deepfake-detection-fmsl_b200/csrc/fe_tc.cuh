@@ -29,11 +29,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef FE_GEMM_TRACE
+__device__ int* g_fe_host_flag = nullptr;
+#endif
 // Bounded wait: a protocol bug turns into a reported error + trap instead of a hung GPU.
 __device__ __noinline__ void mbar_timeout(int* error_flag, int code) {
 #ifdef FE_GEMM_TRACE
-  // debug build: record who timed out first (code * 1000 + warp) and leave, so the flag can be read back
+  // debug build: record who timed out first (code * 1000 + warp) and leave, so the flag can be read back -- also into
+  // host-mapped memory (the context is lost after the tensor-memory leak the early exit causes)
   atomicCAS(error_flag, 0, code * 1000 + (int)(threadIdx.x >> 5));
+  if (g_fe_host_flag && *(volatile int*)g_fe_host_flag == 0) *(volatile int*)g_fe_host_flag = code * 1000 + (int)(threadIdx.x >> 5);
   __threadfence_system();
   asm volatile("exit;");
 #else
