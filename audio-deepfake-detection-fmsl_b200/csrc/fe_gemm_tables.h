@@ -9,7 +9,7 @@ int64_t fe_gemm_plan_layout(const b200fe_params* p, fe_blob_header* h, int64_t o
 // Fills the GEMM tables of a blob whose layout was planned by fe_gemm_plan_layout.
 int32_t fe_gemm_pack(const b200fe_params* p, fe_blob_header* h, const float* window,
                      const float* fbank, char* base);
-// 1 when fe_gemm.cu carries the tcgen05 kernel; AUTO's measured preference (variant selection)
+// 1 when fe_stream.cu carries the tcgen05 kernel; AUTO's measured preference (variant selection)
 bool fe_gemm_variant_built(void);
 bool fe_gemm_auto_prefers(const b200fe_params* p);
 #endif

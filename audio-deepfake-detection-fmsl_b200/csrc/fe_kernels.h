@@ -1,4 +1,4 @@
-// Launch interface of the CUDA-core kernels (fe_kernels.cu) and the tcgen05 kernel (fe_gemm.cu).
+// Launch interface of the CUDA-core kernels (fe_kernels.cu); the tcgen05 streaming kernel (fe_stream.cu) is declared in fe_gemm.h.
 #ifndef FE_KERNELS_H_
 #define FE_KERNELS_H_
 #include <cuda_runtime.h>
