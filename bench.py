@@ -250,6 +250,9 @@ def config4_record(frontend, dev, rank, world):
         scorer(frontend(warm))
     del warm
     if world > 1:
+        # first use of a collective pays NCCL's connection set-up (milliseconds): not part of the gather being timed
+        warm_g = torch.zeros(8 * world, device=dev)
+        dist.all_gather_into_tensor(warm_g, torch.zeros(8, device=dev))
         dist.barrier()
     r = sweep.run_sweep(frontend, scorer, dev, rank=rank, world_size=world)
     t = torch.tensor([r["frontend_ms"], r["classifier_ms"], r["gather_ms"], r["wall_s"] * 1e3], device=dev, dtype=torch.float64)
@@ -282,6 +285,11 @@ def main():
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 also times the reference CPU path on ALL host cores
+    # (cpu_baseline / the reference arm), so its OpenMP / MKL runtimes must start with all of them (before torch loads)
+    if int(os.environ.get("RANK", "0")) == 0:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
