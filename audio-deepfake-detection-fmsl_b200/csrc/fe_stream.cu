@@ -774,13 +774,13 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
     static int* host_flag = nullptr;
     extern int* fe_trace_host_flag;
     if (!host_flag) {
-      cudaHostAlloc((void**)&host_flag, 64, cudaHostAllocMapped);
-      host_flag[0] = 0;
+      cudaHostAlloc((void**)&host_flag, 256, cudaHostAllocMapped);
+      for (int i = 0; i < 64; ++i) host_flag[i] = 0;
       int* dptr = nullptr;
       cudaHostGetDevicePointer((void**)&dptr, host_flag, 0);
       cudaMemcpyToSymbol(g_fe_host_flag, &dptr, sizeof(dptr));
       fe_trace_host_flag = host_flag;
-      static struct printer { int* p; ~printer() { fprintf(stderr, "fe_stream timeout flag (code*1000+warp): %d\n", p[0]); } } pr{host_flag};
+      static struct printer { int* p; ~printer() { fprintf(stderr, "fe_stream timeout codes per warp (code*100000+cta):"); for (int i = 0; i < kThreads / 32; ++i) fprintf(stderr, " w%d:%d", i, p[i]); fprintf(stderr, "\n"); } } pr{host_flag};
     }
   }
   cudaError_t e = cudaMemsetAsync(a.error_flag, 0, 65536, stream);
@@ -789,23 +789,6 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
 #endif
   if (e != cudaSuccess) return e;
   fe_stream_kernel<<<grid, kThreads, smem, stream>>>(*maps_p, a);
-#ifdef FE_GEMM_TRACE
-  {   // debug build: report a protocol timeout as soon as the kernel flags it (the launch may never return afterwards)
-    int* hf = nullptr;
-    cudaMemcpyFromSymbol(&hf, g_fe_host_flag, sizeof(hf));
-    (void)hf;
-    extern int* fe_trace_host_flag;
-    for (int spin = 0; spin < 20000; ++spin) {
-      if (fe_trace_host_flag && fe_trace_host_flag[0]) {
-        fprintf(stderr, "fe_stream timeout flag (code*1000+warp): %d\n", fe_trace_host_flag[0]);
-        fflush(stderr);
-        _exit(3);
-      }
-      if (cudaStreamQuery(stream) != cudaErrorNotReady) break;
-      usleep(1000);
-    }
-  }
-#endif
   *launches = 1;
   return cudaGetLastError();
 }

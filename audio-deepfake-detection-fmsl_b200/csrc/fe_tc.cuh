@@ -35,12 +35,13 @@ __device__ int* g_fe_host_flag = nullptr;
 // Bounded wait: a protocol bug turns into a reported error + trap instead of a hung GPU.
 __device__ __noinline__ void mbar_timeout(int* error_flag, int code) {
 #ifdef FE_GEMM_TRACE
-  // debug build: record who timed out first (code * 1000 + warp) and leave, so the flag can be read back -- also into
-  // host-mapped memory (the context is lost after the tensor-memory leak the early exit causes)
+  // debug build: every warp that times out files its code (host-mapped memory, slot = warp; the launch function prints
+  // them at process exit), lingers so that the others get to file theirs, then traps
   atomicCAS(error_flag, 0, code * 1000 + (int)(threadIdx.x >> 5));
-  if (g_fe_host_flag && *(volatile int*)g_fe_host_flag == 0) *(volatile int*)g_fe_host_flag = code * 1000 + (int)(threadIdx.x >> 5);
+  if (g_fe_host_flag && (threadIdx.x & 31) == 0) ((volatile int*)g_fe_host_flag)[threadIdx.x >> 5] = code * 100000 + (int)blockIdx.x;
   __threadfence_system();
-  asm volatile("exit;");
+  for (int i = 0; i < 4000; ++i) __nanosleep(1000);
+  asm volatile("trap;");
 #else
   atomicExch(error_flag, code);
   __threadfence_system();
