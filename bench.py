@@ -387,11 +387,33 @@ def main():
     e2e = None
     if not args.no_e2e:
         Be = B
-        if world > 1:   # ranks share the host: pin each rank's threads to its own slice of the cores
+        numa_note = None
+        if world > 1:
+            # Ranks share the host.  Pin this rank's threads (and, by first touch, its pinned buffers) to the NUMA node
+            # its GPU hangs off when sysfs tells (round 1: every GPU on node 0, half of the ranks staged through the far
+            # socket); otherwise to its own slice of the cores.
             try:
                 nc = os.cpu_count() or 1
-                per = max(1, nc // world)
-                os.sched_setaffinity(0, range(local_rank * per, min(nc, (local_rank + 1) * per)))
+                cpus = None
+                try:
+                    bus = torch.cuda.get_device_properties(dev).pci_bus_id
+                    dom = torch.cuda.get_device_properties(dev).pci_domain_id
+                    devn = torch.cuda.get_device_properties(dev).pci_device_id
+                    bdf = f"{dom:04x}:{bus:02x}:{devn:02x}.0"
+                    node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+                    if node >= 0:
+                        cpus = set()
+                        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                            lo, _, hi = part.partition("-")
+                            cpus.update(range(int(lo), int(hi or lo) + 1))
+                        numa_note = f"threads and pinned buffers on NUMA node {node} of GPU {bdf} ({len(cpus)} cpus)"
+                except Exception:
+                    cpus = None
+                if not cpus:
+                    per = max(1, nc // world)
+                    cpus = set(range(local_rank * per, min(nc, (local_rank + 1) * per)))
+                    numa_note = f"core slice {min(cpus)}-{max(cpus)} (GPU NUMA node unknown)"
+                os.sched_setaffinity(0, cpus)
             except Exception:
                 pass
         xh = torch.empty(Be, UTT_LEN, dtype=torch.float32, pin_memory=True)
@@ -438,6 +460,7 @@ def main():
         if world > 1:
             dist.all_reduce(pk, op=dist.ReduceOp.MIN)
         h2d_i16 = Be * UTT_LEN * 2
+        e2e_numa_note = numa_note
         d2h = Be * W["n_out"] * W["n_frames"] * 4
         e2e = {"value": v_i16, "unit": "utterances/s",
                "h2d_bytes_per_step": h2d_i16, "d2h_bytes_per_step": d2h, "steps": ke,
@@ -450,7 +473,8 @@ def main():
                              "h2d_gbs_achieved_per_gpu_f32_in": v_f32 / world * UTT_LEN * 4 / 1e9,
                              "h2d_peak_gbs": float(pk[0]), "d2h_peak_gbs": float(pk[1]),
                              "peak_source": "pinned 1 GB torch copy_ per direction, best of 3, min over ranks, all ranks copying at once",
-                             "frac_of_h2d_peak_f32_in": v_f32 / world * UTT_LEN * 4 / 1e9 / max(1e-9, float(pk[0]))}}
+                             "frac_of_h2d_peak_f32_in": v_f32 / world * UTT_LEN * 4 / 1e9 / max(1e-9, float(pk[0])),
+                             "host_placement": e2e_numa_note}}
         del xh, xi, oh
 
     # ---- config 4 sub-record: the 71,237-utterance sweep strong-scaled over the ranks + the score gather ----

@@ -87,3 +87,28 @@ def test_emulated_gemm_other_geometry(fe):
     e = emulate_gemm_energies(m, x)
     ref = _ref_energies(x, 256, 128, 64, 10)
     assert np.abs(e - ref).max() <= 3e-6 * ref.max()
+
+
+def test_drain_tables_qualification_rules(fe):
+    """The drain stores a finished filter segment as the filter's final energy, so the packer must refuse banks
+    where that does not hold (fe_gemm_tables.cpp: pack_drain_tables): AUTO then takes the FFT variant and an
+    explicit dft_gemm request raises."""
+    import torch
+    base = dict(sample_rate=16000, speckwargs=dict(n_fft=512, win_length=320, hop_length=160))
+    # 20 .. 32 linear filters: every class segment is >= 8 columns wide -> qualifies
+    for nf in (20, 24, 32):
+        assert fe.LFCC(n_filter=nf, n_lfcc=nf, **base).engine.resolved_variant() == "dft_gemm", nf
+    # f_max far below Nyquist: the upper filters get no bin at all / the top bins carry no filter
+    m = fe.LFCC(n_filter=20, n_lfcc=20, f_max=1000.0, **base)
+    assert m.engine.resolved_variant() in ("fft", "dft_gemm")
+    x = synth.s1_noise(2, 8000, seed=5)
+    if m.engine.resolved_variant() == "dft_gemm":       # whatever the packer decided must be numerically right
+        e = emulate_gemm_energies(m, x)
+        spec = O.power_spectrogram(x.astype(np.float64), 512, 320, 160, window=O.hann_window(320, np.float64))
+        ref = O.apply_fbank(spec, O.linear_fbanks(257, 0.0, 1000.0, 20, 16000).astype(np.float64))
+        assert np.abs(e - ref).max() <= 3e-6 * ref.max()
+    # a mel bank on the LFCC geometry: narrow low filters (several boundaries per 8-column window) -> refused
+    mel = fe.MelSpectrogram(16000, n_fft=512, win_length=320, hop_length=160, n_mels=32)
+    assert mel.engine.resolved_variant() == "fft"
+    with pytest.raises(NotImplementedError):
+        fe.MelSpectrogram(16000, n_fft=512, win_length=320, hop_length=160, n_mels=32, variant="dft_gemm")
