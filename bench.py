@@ -203,9 +203,15 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))    # (a parent may have pinned itself to a core slice)
+    except Exception:
+        pass
     import torch
     w = WORKLOADS[args.workload]
     per_step_budget = max(0.25, min(15.0, 100.0 / max(1, args.steps + args.warmup)))   # whole arm: <= ~100 s
+    if args.steps == 1:
+        per_step_budget = min(per_step_budget, max(0.25, args.cpu_budget))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     for _ in range(args.warmup):
@@ -251,8 +257,10 @@ def config4_record(frontend, dev, rank, world):
     del warm
     if world > 1:
         # first use of a collective pays NCCL's connection set-up (milliseconds): not part of the gather being timed
-        warm_g = torch.zeros(8 * world, device=dev)
-        dist.all_gather_into_tensor(warm_g, torch.zeros(8, device=dev))
+        from b200_frontend import gather_scores as _gs, shard_range as _sr
+        lo_w, hi_w = _sr(sweep.N_EVAL, rank, world)
+        for _ in range(2):
+            _gs(torch.zeros(hi_w - lo_w, device=dev), sweep.N_EVAL)
         dist.barrier()
     r = sweep.run_sweep(frontend, scorer, dev, rank=rank, world_size=world)
     t = torch.tensor([r["frontend_ms"], r["classifier_ms"], r["gather_ms"], r["wall_s"] * 1e3], device=dev, dtype=torch.float64)
@@ -541,10 +549,22 @@ def main():
                                  "peak_source": "SMs x 128 lanes x 2 (FMA) x max SM clock (nominal)"}
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        thr, threads, n = cpu_reference_throughput(args.workload, args.cpu_budget, threads=os.cpu_count() or 1)
-        cpu_baseline = {"value": thr, "unit": "utterances/s", "cores": threads, "kind": "reference",
-                        "sample": f"torchaudio {args.workload} path on host, {n} S1 utterances in B=64 chunks, "
-                                  f"{threads} threads ({os.cpu_count()} logical cores)"}
+        if world > 1:
+            # Under torchrun this process was started with OMP_NUM_THREADS=1 and has pinned itself to a core slice for
+            # the e2e leg; whatever is set afterwards, its OpenMP pool ran the reference single-threaded (324 utt/s at
+            # N = 2 against 4.8 k at N = 1).  A fresh process with all cores gives the same figure at every N.
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                                  "--workload", args.workload, "--cpu-budget", str(args.cpu_budget)],
+                                 env=env, capture_output=True, text=True, timeout=300)
+            ref_line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+            cpu_baseline = dict(ref_line["cpu_baseline"])
+            cpu_baseline["sample"] += " (fresh process, all host cores)"
+        else:
+            thr, threads, n = cpu_reference_throughput(args.workload, args.cpu_budget, threads=os.cpu_count() or 1)
+            cpu_baseline = {"value": thr, "unit": "utterances/s", "cores": threads, "kind": "reference",
+                            "sample": f"torchaudio {args.workload} path on host, {n} S1 utterances in B=64 chunks, "
+                                      f"{threads} threads ({os.cpu_count()} logical cores)"}
     line = {
         "metric": "utterances/sec (4 s, 16 kHz) LFCC+delta+delta-delta front-end" if args.workload.startswith("lfcc")
         else "utterances/sec (4 s, 16 kHz) 80-bin log-mel front-end",

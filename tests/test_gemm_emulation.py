@@ -112,3 +112,18 @@ def test_drain_tables_qualification_rules(fe):
     assert mel.engine.resolved_variant() == "fft"
     with pytest.raises(NotImplementedError):
         fe.MelSpectrogram(16000, n_fft=512, win_length=320, hop_length=160, n_mels=32, variant="dft_gemm")
+
+
+@pytest.mark.parametrize("n_mels", [10, 16, 20])
+def test_emulated_gemm_energies_mel_bank_on_the_lfcc_geometry(fe, n_mels):
+    """A mel bank (segments of very different widths, filter-less bins at the top) through the tensor-core variant's
+    tables and drain: n_fft 512 / win 320 / hop 160 with few enough mel filters qualifies (AUTO picks dft_gemm)."""
+    m = fe.MelSpectrogram(16000, n_fft=512, win_length=320, hop_length=160, n_mels=n_mels, variant="dft_gemm")
+    assert m.engine.resolved_variant() == "dft_gemm"
+    x = np.concatenate([synth.s1_noise(1, 8000, seed=n_mels), synth.s2_speechlike(1, 8000, seed=n_mels)], 0)
+    e = emulate_gemm_energies(m, x)
+    spec = O.power_spectrogram(x.astype(np.float64), 512, 320, 160, window=O.hann_window(320, np.float64))
+    ref = O.apply_fbank(spec, O.melscale_fbanks(257, 0.0, 8000.0, n_mels, 16000).astype(np.float64))
+    assert e.shape == ref.shape
+    for r in range(2):
+        assert np.abs(e[r] - ref[r]).max() <= 3e-6 * ref[r].max(), (n_mels, r)

@@ -274,3 +274,22 @@ def test_device_eer_in_the_sweep_equals_the_host_restatement(fe):
     r = sweep.run_sweep(fe.LFCCDelta(**LFCC_CFG), scorer, dev(), n_total=3000, n_bonafide=310, batch=512)
     assert (r["eer"], r["min_dcf"], r["eer_threshold"]) == (r["eer_host"], r["min_dcf_host"], r["eer_threshold_host"])
     assert _sk_metrics(sweep.labels(3000, 310), r["scores"]) == (r["eer"], r["min_dcf"], r["eer_threshold"])
+
+
+@pytest.mark.parametrize("n_mels", [10, 20])
+def test_mel_bank_through_the_tensor_core_variant(fe, n_mels):
+    """MelSpectrogram on the LFCC geometry (n_fft 512, win 320, hop 160): mel banks with few filters qualify for the
+    tcgen05 variant (non-uniform segments, filter-less top bins); dB features against torchaudio, and bit-equal
+    energies... between the two kernel families within the stage tolerance."""
+    import torchaudio
+    x = torch.from_numpy(np.concatenate([synth.s1_noise(5, seed=n_mels), synth.s3_edge()[[0, 1, 3]]], 0))
+    ref_t = torch.nn.Sequential(torchaudio.transforms.MelSpectrogram(16000, n_fft=512, win_length=320, hop_length=160, n_mels=n_mels),
+                                torchaudio.transforms.AmplitudeToDB("power", top_db=80.0))
+    ref = ref_t(x.unsqueeze(1)).squeeze(1).numpy()
+    outs = {}
+    for variant in ("dft_gemm", "fft"):
+        m = fe.MelSpectrogram(16000, n_fft=512, win_length=320, hop_length=160, n_mels=n_mels, log="db", variant=variant)
+        assert m.engine.resolved_variant() == variant
+        outs[variant] = m(x.to(dev())).cpu().numpy()
+        assert outs[variant].shape == ref.shape
+        assert (feat_err(outs[variant], ref) <= TOL).all(), (variant, n_mels, feat_err(outs[variant], ref))
