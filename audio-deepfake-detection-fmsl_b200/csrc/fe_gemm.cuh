@@ -91,12 +91,17 @@ FE_HD fe_f2 fe_fma2(fe_f2 a, fe_f2 b, fe_f2 c) {
 // v - fp16(v) (exact in fp32): the hi / lo operands of the split-fp16 products.
 FE_HD void fe_split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
 #ifdef __CUDA_ARCH__
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 back = __half22float2(h);
-  const float2 r = __ffma2_rn(back, make_float2(-1.0f, -1.0f), make_float2(a, b));   // (a, b) - back, exact
-  const __half2 l = __floats2half2_rn(r.x, r.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  // cvt.rn.f16x2 for the hi pair, then the residuals with the sm_100 mixed-precision FMA (FHFMA: fp16 x fp16 + fp32 ->
+  // fp32): fma(h, -1, v) = v - h, exact in fp32 -- one instruction per value instead of unpack + subtract
+  uint32_t h, l;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+  float ra, rb;
+  asm("{\n\t.reg .b16 h0, h1, m1;\n\tmov.b32 {h0, h1}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %0, h0, m1, %3;\n\tfma.rn.f32.f16 %1, h1, m1, %4;\n\t}\n"
+      : "=f"(ra), "=f"(rb) : "r"(h), "f"(a), "f"(b));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(rb), "f"(ra));
+  hi = h;
+  lo = l;
 #else
   float ra, rb;
   hi = fe_pack_hi(a, b, ra, rb);
@@ -155,12 +160,26 @@ FE_HD void fe_stream_produce_unit(const float* fwd, const float* bwd, float scal
   for (int w = 0; w < 4; ++w) {
     const int i0 = 4 * w;
     float ae[4], ao[4];
+#ifdef __CUDA_ARCH__
+    // the same fused multiply-adds, two lanes per issue slot (FMUL2 / FFMA2)
+#pragma unroll
+    for (int u = 0; u < 4; u += 2) {
+      const fe_f2 s2 = fe_f2{scale, scale};
+      const fe_f2 f2 = fe_f2{fwd[i0 + u], fwd[i0 + u + 1]};
+      const fe_f2 bs = fe_mul2(fe_f2{bwd[i0 + u], bwd[i0 + u + 1]}, s2);
+      const fe_f2 e = fe_fma2(f2, s2, bs);
+      const fe_f2 o = fe_fma2(f2, s2, fe_f2{-bs.x, -bs.y});
+      ae[u] = e.x; ae[u + 1] = e.y;
+      ao[u] = o.x; ao[u + 1] = o.y;
+    }
+#else
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float bs = bwd[i0 + u] * scale;
       ae[u] = fmaf(fwd[i0 + u], scale, bs);
       ao[u] = fmaf(fwd[i0 + u], scale, -bs);
     }
+#endif
     const float m0 = midc[i0], m1 = midc[i0 + 1], m2 = midc[i0 + 2], m3 = midc[i0 + 3];
     mid_re = fmaf(ae[0], m0, mid_re);
     mid_im = fmaf(ao[1], m1, mid_im);
