@@ -90,6 +90,9 @@ def run_sweep(frontend: nn.Module, scorer: nn.Module, device: torch.device, *, n
     for a, b, c in timed:
         fe_ms += a.elapsed_time(b)
         cls_ms += b.elapsed_time(c)
+    if dist.is_available() and dist.is_initialized() and world_size > 1:
+        dist.barrier(group)      # rank skew (the slower shard) is not the collective's cost: meet first, then time it
+        torch.cuda.synchronize(device)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     full = gather_scores(local, n_total, group)      # the one collective of the path, timed alone

@@ -212,7 +212,7 @@ def run_reference_arm(args):
     per_step_budget = max(0.25, min(15.0, 100.0 / max(1, args.steps + args.warmup)))   # whole arm: <= ~100 s
     if args.steps == 1:
         per_step_budget = min(per_step_budget, max(0.25, args.cpu_budget))
-    cores = os.cpu_count() or 1
+    cores = int(os.environ.get("B200FE_REF_THREADS", "0")) or os.cpu_count() or 1
     torch.set_num_threads(cores)
     for _ in range(args.warmup):
         cpu_reference_throughput(args.workload, min(0.5, per_step_budget), threads=cores)
@@ -296,8 +296,9 @@ def main():
     # torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 also times the reference CPU path on ALL host cores
     # (cpu_baseline / the reference arm), so its OpenMP / MKL runtimes must start with all of them (before torch loads)
     if int(os.environ.get("RANK", "0")) == 0:
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-        os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
+        nthr_env = os.environ.get("B200FE_REF_THREADS") or str(os.cpu_count() or 1)
+        os.environ["OMP_NUM_THREADS"] = nthr_env
+        os.environ["MKL_NUM_THREADS"] = nthr_env
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -550,16 +551,19 @@ def main():
     cpu_baseline = None
     if not args.no_cpu_baseline:
         if world > 1:
-            # Under torchrun this process was started with OMP_NUM_THREADS=1 and has pinned itself to a core slice for
-            # the e2e leg; whatever is set afterwards, its OpenMP pool ran the reference single-threaded (324 utt/s at
-            # N = 2 against 4.8 k at N = 1).  A fresh process with all cores gives the same figure at every N.
+            # Beside N ranks that spin in their collectives (and this rank's own CUDA / NCCL threads), an OpenMP team as
+            # wide as the machine is oversubscribed and collapses (2 ranks, 24 threads on 24 cores: 0.3 k utt/s against
+            # 4.8 k at N = 1).  A fresh process (clean OpenMP runtime, full affinity) with a few cores left to the ranks
+            # measures the reference on "all the host threads it can use" in this situation.
+            nthr = max(1, (os.cpu_count() or 1) - 3 * world)
             env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+            env["B200FE_REF_THREADS"] = str(nthr)
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
                                   "--workload", args.workload, "--cpu-budget", str(args.cpu_budget)],
                                  env=env, capture_output=True, text=True, timeout=300)
             ref_line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
             cpu_baseline = dict(ref_line["cpu_baseline"])
-            cpu_baseline["sample"] += " (fresh process, all host cores)"
+            cpu_baseline["sample"] += f" (fresh process beside {world} busy ranks, {nthr} of {os.cpu_count()} logical cores)"
         else:
             thr, threads, n = cpu_reference_throughput(args.workload, args.cpu_budget, threads=os.cpu_count() or 1)
             cpu_baseline = {"value": thr, "unit": "utterances/s", "cores": threads, "kind": "reference",
