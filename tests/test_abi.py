@@ -128,3 +128,17 @@ def test_mel_tables(fe):
     m = fe.MelSpectrogram(**MEL_CFG, log="db")
     assert m.engine.n_out == 80 and m.engine.n_frames(64600) == 253
     assert m.engine.resolved_variant() in ("fft", "dft_gemm")
+
+
+def test_eer_entry_point_validates_arguments_without_a_gpu(fe):
+    """b200fe_eer_min_dcf / b200fe_eer_workspace_bytes: sizing and argument checks are host code."""
+    lib = fe._lib.load()
+    assert lib.b200fe_eer_workspace_bytes(71237) >= 2 * 71238 * 8 + 2 * 71238 * 4
+    assert lib.b200fe_eer_workspace_bytes(-1) == -1
+    assert lib.b200fe_eer_min_dcf(None, None, 10, None, None, 0, None) == -1          # NULL pointers
+    assert "b200fe_eer_min_dcf" in fe._lib.last_error()
+    buf = (C.c_char * 64)()
+    assert lib.b200fe_eer_min_dcf(buf, buf, 0, buf, buf, 64, None) == -1               # n < 1
+    assert lib.b200fe_eer_min_dcf(buf, buf, 1000, buf, buf, 64, None) == -3            # workspace too small
+    with pytest.raises(TypeError):
+        fe.eer_min_dcf_device(torch.ones(4, dtype=torch.int64), torch.zeros(4))        # CPU tensors: no fallback
