@@ -163,11 +163,19 @@ class FrontEndEngine:
 
     # -- queries ---------------------------------------------------------------------------------
     def n_frames(self, T: int) -> int:
-        return _lib.check(self.lib.b200fe_n_frames(C.byref(self.params), int(T)))
+        # (memoised: the evaluation loop calls with the same T thousands of times; a ctypes call is ~1.5 us of a 40 us call)
+        c = self.__dict__.setdefault("_nf_cache", {})
+        nf = c.get(T)
+        if nf is None:
+            nf = c[T] = _lib.check(self.lib.b200fe_n_frames(C.byref(self.params), int(T)))
+        return nf
 
     @property
     def n_out(self) -> int:
-        return _lib.check(self.lib.b200fe_n_out_channels(C.byref(self.params)))
+        v = self.__dict__.get("_n_out_cache")
+        if v is None:
+            v = self.__dict__["_n_out_cache"] = _lib.check(self.lib.b200fe_n_out_channels(C.byref(self.params)))
+        return v
 
     def resolved_variant(self) -> str:
         return {1: "fft", 2: "dft_gemm"}[int(self.params.variant)]
@@ -268,9 +276,14 @@ class FrontEndEngine:
         nf = self.n_frames(T)
         if out is None:
             out = torch.empty((R, self.n_out, nf), dtype=torch.float32, device=dev)
-        ws_bytes = _lib.check(self.lib.b200fe_workspace_bytes_ex(C.byref(p), R, T, 0 if offsets is None else 1))
+        wkey = (R, T, offsets is not None, p.variant, p.top_db_group)
+        wc = self.__dict__.setdefault("_ws_bytes_cache", {})
+        ws_bytes = wc.get(wkey)
+        if ws_bytes is None:
+            ws_bytes = wc[wkey] = _lib.check(self.lib.b200fe_workspace_bytes_ex(C.byref(p), R, T, 0 if offsets is None else 1))
         ws = self.workspace_on(dev, ws_bytes)
-        with torch.cuda.device(dev):
+
+        def launch():
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(self.lib.b200fe_features_forward(
                 wave2d.data_ptr(), R, T,
@@ -278,6 +291,11 @@ class FrontEndEngine:
                 None if lengths is None else lengths.data_ptr(),
                 C.byref(p), self.tables_on(dev).data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                 C.c_void_p(stream)))
+        if torch.cuda.current_device() == (dev.index if dev.index is not None else torch.cuda.current_device()):
+            launch()                       # (the device guard costs a few microseconds per call)
+        else:
+            with torch.cuda.device(dev):
+                launch()
         return out
 
     def fbank_energies(self, wave2d: Tensor, out: Optional[Tensor] = None) -> Tensor:
