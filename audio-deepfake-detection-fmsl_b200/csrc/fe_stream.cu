@@ -469,8 +469,13 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           const uint32_t b_base = smem_b + s * b_stage_bytes;
           if (elect_one()) {
             // this warp's sub-GEMMs: A_hi B_hi + A_lo B_hi + A_hi B_lo, alternating accumulators
+#ifdef FE_EXP_TWO_PRODUCTS   // timing experiment: two of the three split-fp16 products (results wrong: what the tensor work costs)
+            constexpr int kProducts = 2;
+#else
+            constexpr int kProducts = 3;
+#endif
 #pragma unroll
-            for (int pr = 0; pr < 3; ++pr) {
+            for (int pr = 0; pr < kProducts; ++pr) {
 #pragma unroll
               for (int ds = 0; ds < 4 / kNumMmaWarps; ++ds) {
                 const int sub = sub0 + ds;
