@@ -12,18 +12,23 @@
 //                     four walkers of a frame meet once per tile for the segments that straddle the column halves and
 //                     bin n_fft/4.  TMEM is released after the last tcgen05.ld.  (A drain warp issues about one
 //                     instruction per five cycles -- dependent packed-FMA chains -- so the drain time is set by how
-//                     many warps share the walk, not by the issue slots: profiles/r2_stream_v3_*.)
-//   16-23  producers  two groups of four warps (lane = frame).  Per tile: max|x| per hop block -> per-frame
-//                     power-of-two scale, then production units (stage, K half): 16 sample pairs of every frame, fold +
-//                     scale + fp16 hi/lo split into the UMMA A tiles; group = K half.  The A slots are not aliased by
-//                     anything, so the first two stages of tile i+1 are produced while tile i is drained.
+//                     many warps share the walk, not by the issue slots: profiles/r2_stream_v3_*.)  Behind the drain,
+//                     while the tensor pipe runs the next tile, these warps scout the tile after that: max|x| per
+//                     hop block straight from global memory -> s_gmax[tile parity] (which also pulls the tile's hop
+//                     blocks into L2 ahead of the loader's TMA boxes).
+//   16-23  producers  two groups of four warps (lane = frame).  Per tile: per-frame power-of-two scale from the
+//                     scouted block maxima, then production units (stage, K half): 16 sample pairs of every frame,
+//                     fold (FMUL2 / FFMA2) + scale + fp16 hi/lo split (cvt.rn.f16x2 + FHFMA residuals) into the UMMA
+//                     A tiles; group = K half.  The A slots are not aliased by anything, so the first two stages of
+//                     tile i+1 are produced while tile i is drained.
 //   24-25  MMA        one issuing thread per sub-GEMM pair (ce, co / se, so): per stage 3 x 2 tcgen05.mma (M=128,
 //                     N=n_fft/4, K=16: hi*hi + lo*hi + hi*lo) into the 4 TMEM accumulators, tcgen05.commit -> mbarriers
 //   26     loader     per tile: the hop blocks the tile's frames need, once each, as a handful of TMA tensor boxes
 //                     {32 floats, hop/32, 2^k hop blocks} with the 128-byte swizzle: hop blocks sit densely in shared
 //                     memory and lane <-> frame reads are still conflict-free.  A small 1-D bulk copy costs the TMA
 //                     unit ~90 cycles whatever its size, hence boxes.  Reflect-padded edge blocks are synthesised
-//                     with plain loads.  Per stage: the 32 KB of DFT operand tiles.
+//                     with plain loads; cp.async.bulk.prefetch.tensor of the next tile's boxes into L2.  Per stage:
+//                     the 32 KB of DFT operand tiles.
 // TMEM holds exactly the four accumulators (4 x 128 columns), so the MMAs of a tile and its drain cannot overlap;
 // the tile period is MMA phase + drain, everything else (sample loads, scout, production, stores) runs beside them.
 #include <atomic>
