@@ -120,3 +120,39 @@ def run_sweep(frontend: nn.Module, scorer: nn.Module, device: torch.device, *, n
                 scores_sha256=hashlib.sha256(scores.astype("<f4").tobytes()).hexdigest(),
                 features_sha256=hashlib.sha256(checks.astype("<i8").tobytes()).hexdigest(),
                 frontend_ms=fe_ms, classifier_ms=cls_ms, gather_ms=gather_ms, wall_s=wall, scores=scores)
+
+
+def score_host_pcm(frontend: nn.Module, scorer: nn.Module, pcm_host: Tensor, device: torch.device, *,
+                   chunk_rows: int = 1024, n_streams: int = 2, out_host: Optional[Tensor] = None) -> Tensor:
+    """The slot use case end to end from HOST memory (maze5.py:297-351 loader -> :415-430 scoring loop): 16-bit PCM
+    rows ``(R, T)`` (pinned) -> host-to-device copy -> ``x / 32768`` (exact) -> front-end -> classifier -> the
+    bonafide score per utterance.  The features never leave the device: 2 bytes per sample go in and 4 bytes per
+    UTTERANCE come back, instead of 388 KB of float32 features per utterance.  Chunks are pipelined over
+    ``n_streams`` streams (copy of one chunk under the kernels of another); returns ``float32[R]`` on the host
+    (pinned).  Scores are those of ``scorer(frontend(pcm / 32768))`` on the same chunks."""
+    if pcm_host.dtype != torch.int16 or pcm_host.dim() != 2 or pcm_host.device.type != "cpu":
+        raise TypeError("score_host_pcm expects a 2-D int16 CPU tensor (16-bit PCM rows)")
+    R, T = pcm_host.shape
+    chunk_rows = max(1, min(int(chunk_rows), R))
+    n_streams = max(1, min(int(n_streams), 4))
+    streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
+    staging = [torch.empty((chunk_rows, T), dtype=torch.int16, device=device) for _ in range(n_streams)]
+    scores = torch.empty(R, dtype=torch.float32, device=device)
+    cur = torch.cuda.current_stream(device)
+    for s in streams:
+        s.wait_stream(cur)
+    for c, r0 in enumerate(range(0, R, chunk_rows)):
+        nr = min(chunk_rows, R - r0)
+        s = streams[c % n_streams]
+        with torch.cuda.stream(s), torch.no_grad():
+            d = staging[c % n_streams][:nr]
+            d.copy_(pcm_host[r0:r0 + nr], non_blocking=True)
+            x = d.to(torch.float32).mul_(1.0 / 32768.0)             # exact: int16 -> float32, times 2^-15
+            scores[r0:r0 + nr] = scorer(frontend(x))[:, 1]          # maze5.py:425
+    for s in streams:
+        cur.wait_stream(s)
+    if out_host is None:
+        out_host = torch.empty(R, dtype=torch.float32, pin_memory=True)
+    out_host.copy_(scores, non_blocking=True)
+    cur.synchronize()
+    return out_host

@@ -448,6 +448,33 @@ def main():
         v_i16 = timed_host(xi)
         v_f32 = timed_host(xh)
 
+        # the slot use case from host memory (informational): PCM in, front-end + maze5 classifier on the device, one
+        # score per utterance back -- the features never cross PCIe (sweep.score_host_pcm)
+        scores_only = None
+        if args.workload == "lfcc":
+            import b200_frontend as _fe
+            from importlib import import_module
+            _sweep = import_module("audio-deepfake-detection-fmsl_b200.sweep")
+            _sc = _fe.MazeScorer(_fe.LFCC_FILTS, fmsl=False)
+            _fe.fill_deterministic(_sc, _sweep.SEED)
+            _sc.to(dev).eval()
+            sh = torch.empty(Be, dtype=torch.float32, pin_memory=True)
+            _sweep.score_host_pcm(mod, _sc, xi, dev, chunk_rows=1024, n_streams=2, out_host=sh)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                _sweep.score_host_pcm(mod, _sc, xi, dev, chunk_rows=1024, n_streams=2, out_host=sh)
+            el = time.perf_counter() - t0
+            te = torch.tensor([el], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            scores_only = {"value": world * Be * 2 / float(te.item()), "unit": "utterances/s",
+                           "h2d_bytes_per_step": Be * UTT_LEN * 2, "d2h_bytes_per_step": Be * 4,
+                           "api": "sweep.score_host_pcm: int16 PCM (host) -> front-end -> maze5 classifier (stock PyTorch / cuDNN, "
+                                  "not part of the accelerated path) -> float32 score per utterance (host)"}
+            del _sc, sh
+
         # pinned-copy peaks of this rank, all ranks copying at once (the N-GPU limiter is the shared host side)
         def copy_peak(dst, src):
             best = 0.0
@@ -483,7 +510,8 @@ def main():
                              "h2d_peak_gbs": float(pk[0]), "d2h_peak_gbs": float(pk[1]),
                              "peak_source": "pinned 1 GB torch copy_ per direction, best of 3, min over ranks, all ranks copying at once",
                              "frac_of_h2d_peak_f32_in": v_f32 / world * UTT_LEN * 4 / 1e9 / max(1e-9, float(pk[0])),
-                             "host_placement": e2e_numa_note}}
+                             "host_placement": e2e_numa_note},
+               "scores_only": scores_only}
         del xh, xi, oh
 
     # ---- config 4 sub-record: the 71,237-utterance sweep strong-scaled over the ranks + the score gather ----

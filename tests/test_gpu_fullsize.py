@@ -293,3 +293,24 @@ def test_mel_bank_through_the_tensor_core_variant(fe, n_mels):
         outs[variant] = m(x.to(dev())).cpu().numpy()
         assert outs[variant].shape == ref.shape
         assert (feat_err(outs[variant], ref) <= TOL).all(), (variant, n_mels, feat_err(outs[variant], ref))
+
+
+def test_scores_from_host_pcm_equal_the_device_path(fe):
+    """sweep.score_host_pcm: 16-bit PCM in host memory -> scores, features never leaving the device; equal to the
+    classifier on the front-end's features of the converted samples, chunk for chunk."""
+    from importlib import import_module
+    sweep = import_module("audio-deepfake-detection-fmsl_b200.sweep")
+    scorer = fe.MazeScorer(fe.LFCC_FILTS, fmsl=False)
+    fe.fill_deterministic(scorer, sweep.SEED)
+    scorer.to(dev()).eval()
+    front = fe.LFCCDelta(**LFCC_CFG)
+    rs = np.random.RandomState(11)
+    pcm = torch.from_numpy(rs.randint(-20000, 20000, size=(700, 64600)).astype(np.int16)).pin_memory()
+    got = sweep.score_host_pcm(front, scorer, pcm, dev(), chunk_rows=256, n_streams=2)
+    assert got.shape == (700,) and got.dtype == torch.float32 and got.device.type == "cpu"
+    x = (pcm.to(torch.float32) / 32768.0).to(dev())
+    with torch.no_grad():
+        want = torch.cat([scorer(front(x[i:i + 256]))[:, 1] for i in range(0, 700, 256)]).cpu()
+    assert torch.equal(got, want)
+    with pytest.raises(TypeError):
+        sweep.score_host_pcm(front, scorer, pcm.to(torch.float32), dev())
