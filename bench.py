@@ -451,7 +451,7 @@ def main():
         # the slot use case from host memory (informational): PCM in, front-end + maze5 classifier on the device, one
         # score per utterance back -- the features never cross PCIe (sweep.score_host_pcm)
         scores_only = None
-        if args.workload == "lfcc":
+        if args.workload == "lfcc" and world == 1:   # (one GPU: the figure is the classifier's, it does not say anything per N)
             import b200_frontend as _fe
             from importlib import import_module
             _sweep = import_module("audio-deepfake-detection-fmsl_b200.sweep")
