@@ -1,3 +1,7 @@
+#!/bin/bash
+# Round-end evidence on one B200 (run under gpurun from the repo root): bench records of the other workloads, the ncu
+# launch list of a short bench, ncu --set full captures of the stream and tail kernels (each only behind a plain run of
+# the same command, as /opt/skills/guides/B200_PROFILING.md asks).  tools/ncu_summary.py turns them into profiles/.
 set -x
 B="python bench.py"
 $B --workload mel --no-config4 > gpurun_out/r2_mel_bench_8192.json 2> gpurun_out/r2_mel.err
@@ -10,4 +14,4 @@ python tests/cuda/gemm_prof.py dft_gemm 1184 > gpurun_out/plain_gemm.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:fe_stream -s 3 -c 1 -o gpurun_out/r2_final_stream python tests/cuda/gemm_prof.py dft_gemm 1184 > gpurun_out/ncu_stream.log 2>&1
 python tests/cuda/tail_prof.py > gpurun_out/plain_tail.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:fe_tail -s 2 -c 1 -o gpurun_out/r2_final_tail python tests/cuda/tail_prof.py > gpurun_out/ncu_tail.log 2>&1
-tail -2 gpurun_out/plain_gemm.log gpurun_out/plain_tail.log
+tail -n 2 gpurun_out/plain_gemm.log; tail -n 2 gpurun_out/plain_tail.log
