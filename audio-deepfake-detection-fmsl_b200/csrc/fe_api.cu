@@ -264,7 +264,10 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
   ta.top_db = p->top_db;
   ta.tt = pick_tt(n_frames);
   ta.halo = p->deltas * ((ta.delta_win - 1) / 2);
-  ta.force_generic = getenv("B200FE_GENERIC_TAIL") != nullptr;  // test hook: compare the two tail kernels
+  {  // test hook: compare the tail kernels (B200FE_GENERIC_TAIL=1: fe_tail_kernel, =fast: fe_tail_fast_kernel)
+    const char* g = getenv("B200FE_GENERIC_TAIL");
+    ta.force_generic = g ? (g[0] == 'f' ? 2 : 1) : 0;
+  }
   if (fe_tail_smem_bytes(ta) > 200 * 1024) {
     fe_set_error("n_filter=%d n_coef=%d does not fit the tail kernel's shared memory", p->n_filter, p->n_coef);
     return B200FE_ERR_UNSUPPORTED;

@@ -700,6 +700,161 @@ __global__ void __launch_bounds__(256) fe_tail_fast_kernel(fe_tail_args a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fe_tail_quad_kernel : fe_tail_fast_kernel's arithmetic for the shape the LFCC front-end runs at (DCT present, channel
+// count a multiple of 4, delta half-width 2 or no deltas, n_frames % 4 == 0) with the instruction count cut to what
+// the feature write-out (three quarters of the step's HBM bytes) can hide:
+//   phase 1  one thread per tile position: the frame's energies fetched with cp.async into the rows the deltas use
+//            later (no staging buffer of their own: 5 CTAs per SM instead of 4), one MUFU per logarithm, the DCT against the table in shared memory (torchaudio's float32 table is not symmetric
+//            under f -> n_filter-1-f to better than 4e-6, so folding the filter pairs would cost parity),
+//            coefficients to shared memory;
+//   phase 2/3  one thread per (channel, four consecutive positions): three 16-byte shared loads give the 8-wide
+//            window of the two-tap-pair stencil, the four results leave as one 16-byte store (coefficients and
+//            deltas in phase 2, delta-deltas in phase 3).
+// Positions outside the utterance hold the clamped frame's values (replicate padding, torchaudio ComputeDeltas).
+// Shared rows are [4 pad | w | 4 pad] floats so that the window loads of the first and last quad stay in bounds.
+// grid (tiles, rows); tt % 4 == 0, halo in {0, 4}.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lg2_normal(float x) {   // x is never subnormal here: plain MUFU.LG2
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float quad_log_energy(float v, int log_mode, float floor_db) {
+  if (log_mode == B200FE_LOG_DB) {
+    v = fmaxf(3.0102999566398120f * lg2_normal(fmaxf(v, 1e-10f)), floor_db);
+  } else if (log_mode == B200FE_LOG_LN) {
+    v = 0.6931471805599453f * lg2_normal(v + 1e-6f);
+  }
+  return v;
+}
+// the stencil sum_m m x[m] / 10 (m = -2 .. 2) at four consecutive positions; a, b, c = x[-4..-1], x[0..3], x[4..7]
+__device__ __forceinline__ float4 quad_delta(const float4 a, const float4 b, const float4 c, float inv_denom) {
+  float4 d;
+  d.x = fmaf(2.0f, b.z - a.z, b.y - a.w) * inv_denom;
+  d.y = fmaf(2.0f, b.w - a.w, b.z - b.x) * inv_denom;
+  d.z = fmaf(2.0f, c.x - b.x, b.w - b.y) * inv_denom;
+  d.w = fmaf(2.0f, c.y - b.y, c.x - b.z) * inv_denom;
+  return d;
+}
+
+#ifndef FE_QUAD_UNROLL
+#define FE_QUAD_UNROLL 4
+#define FE_QUAD_QUAL __maxnreg__(56)   // 5 CTAs of 224 threads per SM
+#endif
+#define FE_PRAGMA(x) _Pragma(#x)
+#define FE_UNROLL(n) FE_PRAGMA(unroll n)
+template <int KQ>
+__global__ void FE_QUAD_QUAL fe_tail_quad_kernel(fe_tail_args a) {
+  constexpr int kRegs = 4 * KQ;   // = n_coef
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tt = a.tt, halo = a.halo, w = tt + 2 * halo, ws = w + 8;
+  const int nfil = a.n_filter;
+  float* s_dct = reinterpret_cast<float*>(smem_raw);   // [nfil][kRegs]
+  float* s_c = s_dct + nfil * kRegs + 4;               // [kRegs][ws], position 0 at +4
+  float* s_d = s_c + kRegs * ws;
+
+  const int j = threadIdx.x;
+  const int64_t row_local = blockIdx.y;
+  const int64_t row = a.row_base + row_local;
+  const int t0 = blockIdx.x * tt;
+  const int nF = a.n_frames;
+  const int tv0 = t0 - halo;
+  const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;
+  // the frame's energies come from L2 / HBM (a microsecond under load): all the fetches start now, as cp.async so
+  // that none of them holds a register; they land in the rows the deltas use later (s_d: free until phase 2)
+  if (j < w) {
+    const float* src = a.energies + (size_t)row_local * nfil * nF + (tv0 + tcl);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_d + j);
+    for (int f = 0; f < nfil; ++f)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(f * ws) * 4u), "l"(src + (size_t)f * nF) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
+  const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
+  {
+    const float4* gd = reinterpret_cast<const float4*>(blob + h->off_dct);   // [nfil][kRegs] floats, 16-byte aligned
+    const int n4 = nfil * KQ;
+    for (int i = j; i < n4; i += blockDim.x) reinterpret_cast<float4*>(s_dct)[i] = gd[i];
+  }
+  float floor_db = -INFINITY;
+  if (a.log_mode == B200FE_LOG_DB && a.top_db >= 0.0f) {
+    const float gmax = __uint_as_float(a.group_max[row / a.top_db_group]);
+    floor_db = 3.0102999566398120f * lg2_normal(fmaxf(gmax, 1e-10f)) - a.top_db;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  if (j < w) {
+    float c[kRegs];
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k) c[k] = 0.0f;
+    const float* ej = s_d + j;   // each thread reads what it fetched itself
+    const float4* dr = reinterpret_cast<const float4*>(s_dct);
+FE_UNROLL(FE_QUAD_UNROLL)
+    for (int f = 0; f < nfil; ++f, dr += KQ) {
+      const float v = quad_log_energy(ej[f * ws], a.log_mode, floor_db);
+#pragma unroll
+      for (int k4 = 0; k4 < KQ; ++k4) {
+        const float4 d = dr[k4];
+        c[4 * k4 + 0] = fmaf(v, d.x, c[4 * k4 + 0]);
+        c[4 * k4 + 1] = fmaf(v, d.y, c[4 * k4 + 1]);
+        c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
+        c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
+      }
+    }
+    float* sc = s_c + j;
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k) sc[k * ws] = c[k];
+  }
+  __syncthreads();
+
+  // (channel, quad) items: quad q of the tile = positions 4q .. 4q+3, channels kl, kl+4, ...
+  const int nqt = blockDim.x >> 2;
+  const int q = j % nqt, kl = j / nqt;
+  const int p0 = 4 * q;
+  const bool in_tile = p0 < w;
+  const bool owner = p0 >= halo && p0 < halo + tt && tv0 + p0 < nF;   // whole quads: tt, halo, nF are multiples of 4
+  float* out_q = a.out + (size_t)row * a.n_out * nF + (tv0 + p0);
+  const float inv_denom = 0.1f;   // 3 / (n (n+1) (2n+1)), n = 2
+  if (a.deltas == 0) {
+    if (owner)
+      for (int k = kl; k < kRegs; k += 4)
+        *reinterpret_cast<float4*>(out_q + (size_t)k * nF) = *reinterpret_cast<const float4*>(s_c + k * ws + p0);
+    return;
+  }
+  if (in_tile) {
+    for (int k = kl; k < kRegs; k += 4) {
+      const float4* p = reinterpret_cast<const float4*>(s_c + k * ws + p0);
+      const float4 b = p[0];
+      const float4 d = quad_delta(p[-1], b, p[1], inv_denom);
+      *reinterpret_cast<float4*>(s_d + k * ws + p0) = d;
+      if (owner) {
+        *reinterpret_cast<float4*>(out_q + (size_t)k * nF) = b;
+        *reinterpret_cast<float4*>(out_q + (size_t)(kRegs + k) * nF) = d;
+      }
+    }
+  }
+  if (a.deltas < 2) return;
+  __syncthreads();
+  if (tv0 < 0 || tv0 + w > nF) {   // block-uniform: the tile reaches over an end of the utterance
+    // replicate padding of the delta series: positions outside the utterance take the delta at the clamped frame
+    if (j < w && tcl != j) {
+      const float* from = s_d + tcl;
+      float* to = s_d + j;
+#pragma unroll 4
+      for (int k = 0; k < kRegs; ++k) to[k * ws] = from[k * ws];
+    }
+    __syncthreads();
+  }
+  if (owner) {
+    for (int k = kl; k < kRegs; k += 4) {
+      const float4* p = reinterpret_cast<const float4*>(s_d + k * ws + p0);
+      *reinterpret_cast<float4*>(out_q + (size_t)(2 * kRegs + k) * nF) = quad_delta(p[-1], p[0], p[1], inv_denom);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fe_cmvn_kernel : one warp per (row, channel); in place
 // ------------------------------------------------------------------------------------------------
 __global__ void fe_cmvn_kernel(float* out, int64_t n_series, int n_frames, float eps) {
@@ -958,8 +1113,54 @@ static void (*pick_tail_fast(int kq))(fe_tail_args) {
   }
 }
 
+// fe_tail_quad_kernel where its shape conditions hold (the LFCC configurations of SURVEY.md 8: 20 coefficients,
+// win_length 5 deltas, 404 frames); false: not applicable, the caller goes on to fe_tail_fast_kernel
+static bool launch_tail_quad(const fe_tail_args& a_in, int64_t rows, cudaStream_t stream, cudaError_t* err) {
+  fe_tail_args a = a_in;
+  const int nc = a.n_coef;
+  if (nc < 4 || (nc & 3) || (a.n_frames & 3) || (reinterpret_cast<uintptr_t>(a.out) & 15)) return false;
+  if (a.deltas > 0 && a.delta_win != 5) return false;
+  a.halo = a.deltas > 0 ? 4 : 0;   // deltas = 1 needs 2: rounded up to whole quads
+  const int max_tt = 256 - 2 * a.halo;
+  const int tiles = (a.n_frames + max_tt - 1) / max_tt;
+  a.tt = (((a.n_frames + tiles - 1) / tiles) + 3) & ~3;
+  const int w = a.tt + 2 * a.halo;
+  const int threads = (w + 31) & ~31;
+  // table, coefficient rows, delta rows (which first receive the n_filter energy rows)
+  const size_t smem = ((size_t)a.n_filter * nc + 4 + (size_t)(nc + (nc > a.n_filter ? nc : a.n_filter)) * (w + 8) + 4) * 4;
+  typedef void (*kern_t)(fe_tail_args);
+  kern_t kern;
+  switch (nc >> 2) {
+    case 1: kern = fe_tail_quad_kernel<1>; break;
+    case 2: kern = fe_tail_quad_kernel<2>; break;
+    case 3: kern = fe_tail_quad_kernel<3>; break;
+    case 4: kern = fe_tail_quad_kernel<4>; break;
+    case 5: kern = fe_tail_quad_kernel<5>; break;
+    case 6: kern = fe_tail_quad_kernel<6>; break;
+    case 7: kern = fe_tail_quad_kernel<7>; break;
+    default: kern = fe_tail_quad_kernel<8>; break;
+  }
+  *err = set_smem((const void*)kern, smem);
+  if (*err != cudaSuccess) return true;
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+    fe_tail_args b = a;
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    b.row_base = a.row_base + r0;
+    b.energies = a.energies + (size_t)r0 * a.n_filter * a.n_frames;
+    dim3 grid((unsigned)tiles, (unsigned)nr);
+    kern<<<grid, threads, smem, stream>>>(b);
+    *err = cudaGetLastError();
+    if (*err != cudaSuccess) return true;
+  }
+  return true;
+}
+
 static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cudaStream_t stream) {
   fe_tail_args a = a_in;
+  if (a.force_generic != 2) {   // 2: test hook, fe_tail_fast_kernel where fe_tail_quad_kernel applies
+    cudaError_t e = cudaSuccess;
+    if (launch_tail_quad(a_in, rows, stream, &e)) return e;
+  }
   // tile so that tt + 2*halo fills (almost) a whole number of warps, at most 256 threads
   const int max_tt = 256 - 2 * a.halo;
   const int tiles = (a.n_frames + max_tt - 1) / max_tt;
@@ -991,7 +1192,7 @@ static cudaError_t launch_tail_fast(const fe_tail_args& a_in, int64_t rows, cuda
 }
 
 cudaError_t fe_launch_tail(const fe_tail_args& a, int64_t rows, cudaStream_t stream) {
-  if (a.n_coef == 0 && a.deltas == 0 && !a.force_generic) {
+  if (a.n_coef == 0 && a.deltas == 0 && a.force_generic != 1) {
     const int per_row = a.n_filter * a.n_frames;
     for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
       fe_tail_args b = a;
@@ -1005,7 +1206,7 @@ cudaError_t fe_launch_tail(const fe_tail_args& a, int64_t rows, cudaStream_t str
     }
     return cudaSuccess;
   }
-  if (a.n_filter <= kFastMax && a.n_coef <= kFastMax && !a.force_generic) return launch_tail_fast(a, rows, stream);
+  if (a.n_filter <= kFastMax && a.n_coef <= kFastMax && a.force_generic != 1) return launch_tail_fast(a, rows, stream);
   const size_t smem = fe_tail_smem_bytes(a);
   cudaError_t e = set_smem((const void*)fe_tail_kernel, smem);
   if (e != cudaSuccess) return e;

@@ -34,7 +34,7 @@ struct fe_tail_args {
   int32_t n_frames, n_filter, n_coef, n_out;
   int32_t log_mode, deltas, delta_win, top_db_group;
   int32_t tt, halo;         // frames per CTA, halo frames each side (= deltas * (delta_win-1)/2)
-  int32_t force_generic;    // tests: use fe_tail_kernel even where fe_tail_fast_kernel applies
+  int32_t force_generic;    // tests: 1 = fe_tail_kernel everywhere, 2 = fe_tail_fast_kernel where fe_tail_quad_kernel applies
   float top_db;
 };
 

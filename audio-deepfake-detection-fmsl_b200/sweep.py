@@ -107,8 +107,8 @@ def run_sweep(frontend: nn.Module, scorer: nn.Module, device: torch.device, *, n
             off += n_part
         del x_all, feats_all, parts
     torch.cuda.synchronize(device)
-    for a, b in timed_front:
-        fe_ms += a.elapsed_time(b)
+    front_calls = [a.elapsed_time(b) for a, b in timed_front]
+    fe_ms = float(sum(front_calls))
     for a, b in timed_cls:
         cls_ms += a.elapsed_time(b)
     if dist.is_available() and dist.is_initialized() and world_size > 1:
@@ -140,7 +140,7 @@ def run_sweep(frontend: nn.Module, scorer: nn.Module, device: torch.device, *, n
                 eer_host=host[0], min_dcf_host=host[1], eer_threshold_host=host[2],
                 scores_sha256=hashlib.sha256(scores.astype("<f4").tobytes()).hexdigest(),
                 features_sha256=hashlib.sha256(checks.astype("<i8").tobytes()).hexdigest(),
-                frontend_ms=fe_ms, classifier_ms=cls_ms, gather_ms=gather_ms, wall_s=wall, scores=scores)
+                frontend_ms=fe_ms, frontend_calls_ms=front_calls, classifier_ms=cls_ms, gather_ms=gather_ms, wall_s=wall, scores=scores)
 
 
 def score_host_pcm(frontend: nn.Module, scorer: nn.Module, pcm_host: Tensor, device: torch.device, *,

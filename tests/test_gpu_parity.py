@@ -403,22 +403,37 @@ def test_auto_variant_and_explicit_errors(fe):
 
 
 def test_fast_tail_equals_generic_tail(fe, monkeypatch):
-    """fe_tail_fast_kernel (registers, MUFU logarithms, unrolled stencils) against fe_tail_kernel (the one the
-    CPU emulation covers): the same features to a few float32 ulps."""
+    """fe_tail_quad_kernel (default at 404 frames: 16-byte stencil loads / stores) and
+    fe_tail_fast_kernel (registers, MUFU logarithms, unrolled stencils; B200FE_GENERIC_TAIL=fast, and the default
+    where the quad kernel's shape conditions fail) against fe_tail_kernel (the one the CPU emulation covers): the
+    same features to a few float32 ulps."""
+    def three(m, x):
+        outs = []
+        for hook in (None, "fast", "1"):
+            if hook is None:
+                monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
+            else:
+                monkeypatch.setenv("B200FE_GENERIC_TAIL", hook)
+            outs.append(m(x).cpu().numpy().copy())
+        monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
+        return outs
     x = cuda(np.concatenate([synth.s1_noise(6), synth.s3_edge()], 0))
-    for kw in (dict(deltas=2), dict(deltas=1), dict(deltas=0), dict(deltas=2, log_lf=True)):
-        m = fe.LFCC(**LFCC_CFG, variant="fft", **kw)
-        monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
-        fast = m(x).clone()
-        monkeypatch.setenv("B200FE_GENERIC_TAIL", "1")
-        generic = m(x).clone()
-        monkeypatch.delenv("B200FE_GENERIC_TAIL", raising=False)
-        assert feat_err(fast.cpu().numpy(), generic.cpu().numpy()).max() <= 5e-5, kw   # half the parity tolerance (edge rows sit on the top_db clamp)
-    short = cuda(synth.s1_noise(3, 4000))
-    m = fe.LFCCDelta(**LFCC_CFG, variant="fft")
-    fast = m(short).clone()
-    monkeypatch.setenv("B200FE_GENERIC_TAIL", "1")
-    assert feat_err(fast.cpu().numpy(), m(short).cpu().numpy()).max() <= 5e-5
+    cases = [dict(deltas=2), dict(deltas=1), dict(deltas=0), dict(deltas=2, log_lf=True),
+             dict(deltas=2, n_filter=21),
+             dict(deltas=2, n_lfcc=12, n_filter=24)]
+    for kw in cases:
+        cfg = dict(LFCC_CFG)
+        cfg.update(kw)
+        quad, fast, generic = three(fe.LFCC(**cfg, variant="fft"), x)
+        # half the parity tolerance (edge rows sit on the top_db clamp)
+        assert feat_err(quad, generic).max() <= 5e-5, kw
+        assert feat_err(fast, generic).max() <= 5e-5, kw
+    # frame counts the quad kernel does not take (26 frames) and ones it tiles three ways (604 frames)
+    for n in (4000, 96480):
+        xs = cuda(synth.s1_noise(3, n))
+        quad, fast, generic = three(fe.LFCCDelta(**LFCC_CFG, variant="fft"), xs)
+        assert feat_err(quad, generic).max() <= 5e-5, n
+        assert feat_err(fast, generic).max() <= 5e-5, n
 
 
 def test_pointwise_tail_equals_generic_tail(fe, monkeypatch):
