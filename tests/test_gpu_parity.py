@@ -428,8 +428,9 @@ def test_fast_tail_equals_generic_tail(fe, monkeypatch):
         # half the parity tolerance (edge rows sit on the top_db clamp)
         assert feat_err(quad, generic).max() <= 5e-5, kw
         assert feat_err(fast, generic).max() <= 5e-5, kw
-    # frame counts the quad kernel does not take (26 frames) and ones it tiles three ways (604 frames)
-    for n in (4000, 96480):
+    # frame counts the quad kernel does not take (26 frames), ones it tiles three ways (604 frames) and tiles that are
+    # nearly all halo (4 and 8 frames)
+    for n in (4000, 96480, 480, 1120):
         xs = cuda(synth.s1_noise(3, n))
         quad, fast, generic = three(fe.LFCCDelta(**LFCC_CFG, variant="fft"), xs)
         assert feat_err(quad, generic).max() <= 5e-5, n
