@@ -1118,7 +1118,7 @@ static void (*pick_tail_fast(int kq))(fe_tail_args) {
 static bool launch_tail_quad(const fe_tail_args& a_in, int64_t rows, cudaStream_t stream, cudaError_t* err) {
   fe_tail_args a = a_in;
   const int nc = a.n_coef;
-  if (nc < 4 || (nc & 3) || (a.n_frames & 3) || (reinterpret_cast<uintptr_t>(a.out) & 15)) return false;
+  if (nc < 4 || (nc & 3) || (a.n_frames & 3) || ((reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.tables)) & 15)) return false;
   if (a.deltas > 0 && a.delta_win != 5) return false;
   a.halo = a.deltas > 0 ? 4 : 0;   // deltas = 1 needs 2: rounded up to whole quads
   const int max_tt = 256 - 2 * a.halo;
