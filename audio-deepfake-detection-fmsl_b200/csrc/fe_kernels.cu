@@ -738,37 +738,61 @@ __device__ __forceinline__ float4 quad_delta(const float4 a, const float4 b, con
 }
 
 #ifndef FE_QUAD_UNROLL
-#define FE_QUAD_UNROLL 4
-#define FE_QUAD_QUAL __maxnreg__(56)   // 5 CTAs of 224 threads per SM
+#define FE_QUAD_UNROLL 2
+#define FE_QUAD_QUAL __maxnreg__(KQ <= 6 ? 56 : 80)   // 56: 5 CTAs of 224 threads per SM
 #endif
 #define FE_PRAGMA(x) _Pragma(#x)
 #define FE_UNROLL(n) FE_PRAGMA(unroll n)
-template <int KQ>
-__global__ void FE_QUAD_QUAL fe_tail_quad_kernel(fe_tail_args a) {
+template <int KQ, int NFT>   // NFT: n_filter when it equals the coefficient count 4*KQ (every loop unrolls), else 0
+__global__ void FE_QUAD_QUAL fe_tail_quad_kernel(fe_tail_args a, int tiles_per_row, int n_tiles) {
   constexpr int kRegs = 4 * KQ;   // = n_coef
+  constexpr int kUnrollF = NFT ? NFT : FE_QUAD_UNROLL, kUnrollQ = NFT ? (NFT + 3) / 4 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tt = a.tt, halo = a.halo, w = tt + 2 * halo, ws = w + 8;
-  const int nfil = a.n_filter;
+  const int nfil = NFT ? NFT : a.n_filter;
+  const int nF = a.n_frames;
   float* s_dct = reinterpret_cast<float*>(smem_raw);   // [nfil][kRegs]
   float* s_c = s_dct + nfil * kRegs + 4;               // [kRegs][ws], position 0 at +4
-  float* s_d = s_c + kRegs * ws;
+  float* s_d = s_c + kRegs * ws;                       // [max(kRegs, nfil)][ws]
+  float* s_e = s_d;                                    // [nfil][ws] the tile's energies land in the delta rows (free until phase 2)
 
   const int j = threadIdx.x;
-  const int64_t row_local = blockIdx.y;
-  const int64_t row = a.row_base + row_local;
-  const int t0 = blockIdx.x * tt;
-  const int nF = a.n_frames;
-  const int tv0 = t0 - halo;
-  const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;
-  // the frame's energies come from L2 / HBM (a microsecond under load): all the fetches start now, as cp.async so
-  // that none of them holds a register; they land in the rows the deltas use later (s_d: free until phase 2)
-  if (j < w) {
-    const float* src = a.energies + (size_t)row_local * nfil * nF + (tv0 + tcl);
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_d + j);
-    for (int f = 0; f < nfil; ++f)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(f * ws) * 4u), "l"(src + (size_t)f * nF) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  // (filter | channel, quad) items: quad q of the tile = positions 4q .. 4q+3, rows kl, kl+4, ...
+  const int nqt = blockDim.x >> 2;
+  const int q = j % nqt, kl = j / nqt;
+  const int p0 = 4 * q;
+  const bool in_tile = p0 < w;
+  const float inv_denom = 0.1f;   // 3 / (n (n+1) (2n+1)), n = 2
+
+  // A tile's energies come from L2 / HBM (a microsecond under load).  They are fetched with cp.async (no registers
+  // held), 16 bytes = four frames of one filter each, all issued before anything else.  Quads outside the utterance
+  // take the clamped frame four times (replicate padding).  One tile per CTA: a persistent form of this kernel (CTAs
+  // walking tiles, the next tile's fetch issued under the delta phases, 54 KB -> 4 CTAs per SM) measured 0.139 ms
+  // against 0.125 ms per 4096 utterances: the kernel is bound by the shared-memory pipe and instruction issue
+  // (both ~65 % busy), not by the exposed fetch latency, and the fifth resident CTA is worth more than the overlap.
+  auto fetch = [&](int g) {
+    if (g < n_tiles && in_tile) {
+      const int rl = g / tiles_per_row;
+      const int fr = (g - rl * tiles_per_row) * tt - halo + p0;   // multiple of 4, like n_frames: inside or outside
+      const bool inside = fr >= 0 && fr < nF;
+      const float* src = a.energies + ((size_t)rl * nfil + kl) * nF + (inside ? fr : (fr < 0 ? 0 : nF - 1));
+      uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_e + kl * ws + p0);
+      const size_t src_step = (size_t)4 * nF;
+      const uint32_t dst_step = (uint32_t)ws * 16u;
+      if (inside) {
+#pragma unroll kUnrollQ
+        for (int f = kl; f < nfil; f += 4, src += src_step, dst += dst_step)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      } else {
+        for (int f = kl; f < nfil; f += 4, src += src_step, dst += dst_step)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(blockIdx.x);
   const unsigned char* blob = reinterpret_cast<const unsigned char*>(a.tables);
   const fe_blob_header* h = reinterpret_cast<const fe_blob_header*>(blob);
   {
@@ -776,80 +800,86 @@ __global__ void FE_QUAD_QUAL fe_tail_quad_kernel(fe_tail_args a) {
     const int n4 = nfil * KQ;
     for (int i = j; i < n4; i += blockDim.x) reinterpret_cast<float4*>(s_dct)[i] = gd[i];
   }
-  float floor_db = -INFINITY;
-  if (a.log_mode == B200FE_LOG_DB && a.top_db >= 0.0f) {
-    const float gmax = __uint_as_float(a.group_max[row / a.top_db_group]);
-    floor_db = 3.0102999566398120f * lg2_normal(fmaxf(gmax, 1e-10f)) - a.top_db;
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
 
-  if (j < w) {
-    float c[kRegs];
-#pragma unroll
-    for (int k = 0; k < kRegs; ++k) c[k] = 0.0f;
-    const float* ej = s_d + j;   // each thread reads what it fetched itself
-    const float4* dr = reinterpret_cast<const float4*>(s_dct);
-FE_UNROLL(FE_QUAD_UNROLL)
-    for (int f = 0; f < nfil; ++f, dr += KQ) {
-      const float v = quad_log_energy(ej[f * ws], a.log_mode, floor_db);
-#pragma unroll
-      for (int k4 = 0; k4 < KQ; ++k4) {
-        const float4 d = dr[k4];
-        c[4 * k4 + 0] = fmaf(v, d.x, c[4 * k4 + 0]);
-        c[4 * k4 + 1] = fmaf(v, d.y, c[4 * k4 + 1]);
-        c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
-        c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
-      }
+  {
+    const int g = blockIdx.x;
+    const int row_local = g / tiles_per_row;
+    const int64_t row = a.row_base + row_local;
+    const int t0 = (g - row_local * tiles_per_row) * tt;
+    const int tv0 = t0 - halo;
+    const int tcl = fe_clampi(tv0 + j, 0, nF - 1) - tv0;
+    float floor_db = -INFINITY;
+    if (a.log_mode == B200FE_LOG_DB && a.top_db >= 0.0f) {
+      // (a 64-bit division costs ~80 instructions; the row index of any real batch fits 32 bits)
+      const int64_t grp = a.top_db_group == 1 ? row
+                          : (row >> 32) == 0 ? (int64_t)((uint32_t)row / (uint32_t)a.top_db_group) : row / a.top_db_group;
+      const float gmax = __uint_as_float(a.group_max[grp]);
+      floor_db = 3.0102999566398120f * lg2_normal(fmaxf(gmax, 1e-10f)) - a.top_db;
     }
-    float* sc = s_c + j;
-#pragma unroll
-    for (int k = 0; k < kRegs; ++k) sc[k * ws] = c[k];
-  }
-  __syncthreads();
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();   // the tile's energies and the table are in
 
-  // (channel, quad) items: quad q of the tile = positions 4q .. 4q+3, channels kl, kl+4, ...
-  const int nqt = blockDim.x >> 2;
-  const int q = j % nqt, kl = j / nqt;
-  const int p0 = 4 * q;
-  const bool in_tile = p0 < w;
-  const bool owner = p0 >= halo && p0 < halo + tt && tv0 + p0 < nF;   // whole quads: tt, halo, nF are multiples of 4
-  float* out_q = a.out + (size_t)row * a.n_out * nF + (tv0 + p0);
-  const float inv_denom = 0.1f;   // 3 / (n (n+1) (2n+1)), n = 2
-  if (a.deltas == 0) {
-    if (owner)
-      for (int k = kl; k < kRegs; k += 4)
-        *reinterpret_cast<float4*>(out_q + (size_t)k * nF) = *reinterpret_cast<const float4*>(s_c + k * ws + p0);
-    return;
-  }
-  if (in_tile) {
-    for (int k = kl; k < kRegs; k += 4) {
-      const float4* p = reinterpret_cast<const float4*>(s_c + k * ws + p0);
-      const float4 b = p[0];
-      const float4 d = quad_delta(p[-1], b, p[1], inv_denom);
-      *reinterpret_cast<float4*>(s_d + k * ws + p0) = d;
-      if (owner) {
-        *reinterpret_cast<float4*>(out_q + (size_t)k * nF) = b;
-        *reinterpret_cast<float4*>(out_q + (size_t)(kRegs + k) * nF) = d;
+    if (j < w) {
+      float c[kRegs];
+#pragma unroll
+      for (int k = 0; k < kRegs; ++k) c[k] = 0.0f;
+      const float* ej = s_e + j;
+      const float4* dr = reinterpret_cast<const float4*>(s_dct);
+#pragma unroll kUnrollF
+      for (int f = 0; f < nfil; ++f, dr += KQ, ej += ws) {
+        const float v = quad_log_energy(*ej, a.log_mode, floor_db);
+#pragma unroll
+        for (int k4 = 0; k4 < KQ; ++k4) {
+          const float4 d = dr[k4];
+          c[4 * k4 + 0] = fmaf(v, d.x, c[4 * k4 + 0]);
+          c[4 * k4 + 1] = fmaf(v, d.y, c[4 * k4 + 1]);
+          c[4 * k4 + 2] = fmaf(v, d.z, c[4 * k4 + 2]);
+          c[4 * k4 + 3] = fmaf(v, d.w, c[4 * k4 + 3]);
+        }
       }
-    }
-  }
-  if (a.deltas < 2) return;
-  __syncthreads();
-  if (tv0 < 0 || tv0 + w > nF) {   // block-uniform: the tile reaches over an end of the utterance
-    // replicate padding of the delta series: positions outside the utterance take the delta at the clamped frame
-    if (j < w && tcl != j) {
-      const float* from = s_d + tcl;
-      float* to = s_d + j;
-#pragma unroll 4
-      for (int k = 0; k < kRegs; ++k) to[k * ws] = from[k * ws];
+      float* sc = s_c + j;
+#pragma unroll
+      for (int k = 0; k < kRegs; ++k) sc[k * ws] = c[k];
     }
     __syncthreads();
-  }
-  if (owner) {
-    for (int k = kl; k < kRegs; k += 4) {
-      const float4* p = reinterpret_cast<const float4*>(s_d + k * ws + p0);
-      *reinterpret_cast<float4*>(out_q + (size_t)(2 * kRegs + k) * nF) = quad_delta(p[-1], p[0], p[1], inv_denom);
+
+    const bool owner = p0 >= halo && p0 < halo + tt && tv0 + p0 < nF;   // whole quads: tt, halo, nF are multiples of 4
+    float* out_q = a.out + (size_t)row * a.n_out * nF + (tv0 + p0);
+    if (a.deltas == 0) {
+      if (owner)
+        for (int k = kl; k < kRegs; k += 4)
+          *reinterpret_cast<float4*>(out_q + (size_t)k * nF) = *reinterpret_cast<const float4*>(s_c + k * ws + p0);
+      return;
+    }
+    if (in_tile) {
+      for (int k = kl; k < kRegs; k += 4) {
+        const float4* p = reinterpret_cast<const float4*>(s_c + k * ws + p0);
+        const float4 b = p[0];
+        const float4 d = quad_delta(p[-1], b, p[1], inv_denom);
+        *reinterpret_cast<float4*>(s_d + k * ws + p0) = d;
+        if (owner) {
+          *reinterpret_cast<float4*>(out_q + (size_t)k * nF) = b;
+          *reinterpret_cast<float4*>(out_q + (size_t)(kRegs + k) * nF) = d;
+        }
+      }
+    }
+    if (a.deltas < 2) return;
+    __syncthreads();
+    if (tv0 < 0 || tv0 + w > nF) {   // block-uniform: the tile reaches over an end of the utterance
+      // replicate padding of the delta series: positions outside the utterance take the delta at the clamped frame
+      if (j < w && tcl != j) {
+        const float* from = s_d + tcl;
+        float* to = s_d + j;
+#pragma unroll 4
+        for (int k = 0; k < kRegs; ++k) to[k * ws] = from[k * ws];
+      }
+      __syncthreads();
+    }
+    if (owner) {
+      for (int k = kl; k < kRegs; k += 4) {
+        const float4* p = reinterpret_cast<const float4*>(s_d + k * ws + p0);
+        *reinterpret_cast<float4*>(out_q + (size_t)(2 * kRegs + k) * nF) = quad_delta(p[-1], p[0], p[1], inv_denom);
+      }
     }
   }
 }
@@ -1118,7 +1148,7 @@ static void (*pick_tail_fast(int kq))(fe_tail_args) {
 static bool launch_tail_quad(const fe_tail_args& a_in, int64_t rows, cudaStream_t stream, cudaError_t* err) {
   fe_tail_args a = a_in;
   const int nc = a.n_coef;
-  if (nc < 4 || (nc & 3) || (a.n_frames & 3) || ((reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.tables)) & 15)) return false;
+  if (nc < 4 || (nc & 3) || (a.n_frames & 3) || ((reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.tables) | reinterpret_cast<uintptr_t>(a.energies)) & 15)) return false;
   if (a.deltas > 0 && a.delta_win != 5) return false;
   a.halo = a.deltas > 0 ? 4 : 0;   // deltas = 1 needs 2: rounded up to whole quads
   const int max_tt = 256 - 2 * a.halo;
@@ -1128,27 +1158,30 @@ static bool launch_tail_quad(const fe_tail_args& a_in, int64_t rows, cudaStream_
   const int threads = (w + 31) & ~31;
   // table, coefficient rows, delta rows (which first receive the n_filter energy rows)
   const size_t smem = ((size_t)a.n_filter * nc + 4 + (size_t)(nc + (nc > a.n_filter ? nc : a.n_filter)) * (w + 8) + 4) * 4;
-  typedef void (*kern_t)(fe_tail_args);
+  typedef void (*kern_t)(fe_tail_args, int, int);
   kern_t kern;
+  const bool sq = a.n_filter == nc;   // the square DCT (20 x 20 for the LFCC front-end): n_filter at compile time
   switch (nc >> 2) {
-    case 1: kern = fe_tail_quad_kernel<1>; break;
-    case 2: kern = fe_tail_quad_kernel<2>; break;
-    case 3: kern = fe_tail_quad_kernel<3>; break;
-    case 4: kern = fe_tail_quad_kernel<4>; break;
-    case 5: kern = fe_tail_quad_kernel<5>; break;
-    case 6: kern = fe_tail_quad_kernel<6>; break;
-    case 7: kern = fe_tail_quad_kernel<7>; break;
-    default: kern = fe_tail_quad_kernel<8>; break;
+    case 1: kern = sq ? fe_tail_quad_kernel<1, 4> : fe_tail_quad_kernel<1, 0>; break;
+    case 2: kern = sq ? fe_tail_quad_kernel<2, 8> : fe_tail_quad_kernel<2, 0>; break;
+    case 3: kern = sq ? fe_tail_quad_kernel<3, 12> : fe_tail_quad_kernel<3, 0>; break;
+    case 4: kern = sq ? fe_tail_quad_kernel<4, 16> : fe_tail_quad_kernel<4, 0>; break;
+    case 5: kern = sq ? fe_tail_quad_kernel<5, 20> : fe_tail_quad_kernel<5, 0>; break;
+    case 6: kern = sq ? fe_tail_quad_kernel<6, 24> : fe_tail_quad_kernel<6, 0>; break;
+    case 7: kern = sq ? fe_tail_quad_kernel<7, 28> : fe_tail_quad_kernel<7, 0>; break;
+    default: kern = fe_tail_quad_kernel<8, 0>; break;   // (32 x 32 fully unrolled spills)
   }
   *err = set_smem((const void*)kern, smem);
   if (*err != cudaSuccess) return true;
-  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+  // one CTA per (row, tile), a 1-D grid (no 65535-row limit)
+  const int64_t max_rows = (int64_t)0x3fffffff / tiles;   // tile indices (and index + grid) are 32-bit in the kernel
+  for (int64_t r0 = 0; r0 < rows; r0 += max_rows) {
     fe_tail_args b = a;
-    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    const int64_t nr = rows - r0 < max_rows ? rows - r0 : max_rows;
     b.row_base = a.row_base + r0;
     b.energies = a.energies + (size_t)r0 * a.n_filter * a.n_frames;
-    dim3 grid((unsigned)tiles, (unsigned)nr);
-    kern<<<grid, threads, smem, stream>>>(b);
+    const int64_t n_tiles = nr * tiles;
+    kern<<<(unsigned)n_tiles, threads, smem, stream>>>(b, tiles, (int)n_tiles);
     *err = cudaGetLastError();
     if (*err != cudaSuccess) return true;
   }
