@@ -539,7 +539,7 @@ def main():
     # `frac` is the WHOLE path's algorithmic bytes over the WHOLE step's time.  `dominant_kernel` is the per-kernel
     # view: that kernel's OWN algorithmic bytes (waveform read + what it writes) over its own time, and its DRAM
     # traffic per launch as ncu measured it on the committed build.
-    kname = ("fe_dense_rows_kernel + fe_stream_kernel + fe_tail_fast_kernel (whole step)" if ragged else
+    kname = ("fe_dense_rows_kernel + fe_stream_kernel + fe_tail_quad_kernel (whole step)" if ragged else
              "fe_stream_kernel" if variant == "dft_gemm" else
              ("fe_rfft_kernel<1,16>" if args.workload == "mel" else "fe_rfft_kernel<1,8>"))
     kernel_bytes_per_utt = W["bytes_per_utt"] if ragged else UTT_LEN * 4 + eng.params.n_filter * W["n_frames"] * 4
