@@ -98,6 +98,8 @@ def eer_min_dcf_device(y_true: torch.Tensor, y_score: torch.Tensor, *, sync: boo
     if not sync:
         return out
     eer, dcf, thr, status = out.tolist()
+    if status == 2.0:
+        raise ValueError("scores contain NaN (scikit-learn's roc_curve raises on such input too)")
     if status != 0.0:
         raise ValueError("EER needs both classes present (Maze5_eval.py:577-582 returns {} in that case)")
     return eer, dcf, thr

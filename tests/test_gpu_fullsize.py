@@ -259,6 +259,10 @@ def test_device_eer_equals_sklearn_digit_for_digit(fe, n, decimals):
     assert fe.eer_min_dcf_device(torch.from_numpy(yy).to(dev()), torch.from_numpy(ss).to(dev())) == _sk_metrics(yy, ss)
     with pytest.raises(ValueError):
         fe.eer_min_dcf_device(torch.ones(10, dtype=torch.int64, device=dev()), torch.randn(10, device=dev()))
+    with pytest.raises(ValueError, match="NaN"):     # scikit-learn raises on NaN scores; the kernel reports status 2
+        bad = torch.randn(10, device=dev())
+        bad[3] = float("nan")
+        fe.eer_min_dcf_device(torch.tensor([1, 0] * 5, device=dev()), bad)
     with pytest.raises(TypeError):
         fe.eer_min_dcf_device(torch.ones(10, dtype=torch.int64), torch.randn(10))
 
