@@ -280,13 +280,34 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
     if (variant == B200FE_VARIANT_DFT_GEMM) {
       int launches = 0;
       if (staged) {
-        e = fe_launch_dense_rows(wave, offsets, lengths, r0, nr, T, p->preemph, dense, stream);
+        // Ragged clips that pad() only truncates (len >= T) and that start 16-byte aligned are read where they lie
+        // (the tensor maps then count 16-byte units above the lower of the two buffers); only the others -- short
+        // clips (repeat-pad), unaligned ones, and everything when pre-emphasis is on -- are staged as dense rows.
+        int64_t flat_rel = -1, dense_rel = 0;
+        const float* base = dense;
+        if (offsets && lengths && p->preemph == 0.0f && ((uintptr_t)wave & 15) == 0 && !getenv("B200FE_STAGE_ALL")) {
+          const uintptr_t lo = (uintptr_t)wave < (uintptr_t)dense ? (uintptr_t)wave : (uintptr_t)dense;
+          const int64_t fr = (int64_t)(((uintptr_t)wave - lo) / 4), dr = (int64_t)(((uintptr_t)dense - lo) / 4);
+          if (((dr + nr * T) >> 2) < 0x7ffffff0LL) {
+            base = (const float*)lo;
+            flat_rel = fr;
+            dense_rel = dr;
+          }
+        }
+        e = fe_launch_dense_rows(wave, offsets, lengths, r0, nr, T, p->preemph, dense, stream, flat_rel);
         if (e != cudaSuccess) return cuda_fail(e, "dense-rows kernel launch");
         g_launches += (nr + 65534) / 65535;
         fe_fft_args fs = fa;
         fs.wave_chunk = dense;
-        fs.offsets = nullptr;
-        fs.lengths = nullptr;
+        if (flat_rel >= 0) {
+          fs.wave = base;
+          fs.in_place = 1;
+          fs.flat_rel = flat_rel;
+          fs.dense_rel = dense_rel;
+        } else {
+          fs.offsets = nullptr;
+          fs.lengths = nullptr;
+        }
         e = fe_stream_launch(p, fs, r0, nr, gemm_ws, stream, &launches);
       } else {
         e = fe_stream_launch(p, fa, r0, nr, gemm_ws, stream, &launches);

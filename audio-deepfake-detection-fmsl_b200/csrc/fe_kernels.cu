@@ -934,13 +934,15 @@ __global__ void fe_deltas_kernel(const float* __restrict__ in, float* __restrict
 __global__ void __launch_bounds__(256) fe_dense_rows_kernel(const float* __restrict__ wave,
                                                            const int64_t* __restrict__ offsets,
                                                            const int32_t* __restrict__ lengths, int64_t row_base,
-                                                           int T, float preemph, float* __restrict__ dst) {
+                                                           int T, float preemph, float* __restrict__ dst,
+                                                           int64_t flat_rel) {
   const int64_t row = row_base + blockIdx.y;
   const float* src;
   int clip_len;
   if (offsets) {
     src = wave + offsets[row];
     clip_len = lengths[row];
+    if (fe_clip_in_place(offsets[row], clip_len, T, flat_rel)) return;   // the streaming kernel reads this clip in place
   } else {
     src = wave + row * (int64_t)T;
     clip_len = T;
@@ -1281,13 +1283,16 @@ cudaError_t fe_launch_deltas(const float* in, float* out, int64_t rows, int64_t 
 
 cudaError_t fe_launch_dense_rows(const float* wave, const int64_t* offsets, const int32_t* lengths,
                                  int64_t row_base, int64_t rows, int64_t T, float preemph, float* dst,
-                                 cudaStream_t stream) {
-  const unsigned bx = (unsigned)((T / 4 + 255) / 256);
+                                 cudaStream_t stream, int64_t flat_rel) {
+  // rows the streaming kernel reads in place leave at once: with them in the batch, 8 CTAs per row (each thread walks
+  // the row in 8 steps) instead of one CTA per 1024 samples, so that a skipped row costs 8 empty CTAs, not 64
+  unsigned bx = (unsigned)((T / 4 + 255) / 256);
+  if (flat_rel >= 0 && bx > 8) bx = 8;
   for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
     const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
     dim3 grid(bx, (unsigned)nr);
     fe_dense_rows_kernel<<<grid, 256, 0, stream>>>(wave, offsets, lengths, row_base + r0, (int)T, preemph,
-                                                   dst + r0 * T);
+                                                   dst + r0 * T, flat_rel);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

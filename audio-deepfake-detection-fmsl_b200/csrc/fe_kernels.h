@@ -10,6 +10,10 @@ struct fe_fft_args {
                             // input was staged by fe_launch_dense_rows; NULL: rows are read from `wave`
   const int64_t* offsets;   // ragged: start of each row's clip (floats), else NULL
   const int32_t* lengths;   // ragged: clip lengths, else NULL
+  // streaming kernel, ragged input read partly in place (in_place != 0): `wave` is then the lower of the two buffers,
+  // the flat clip buffer starts flat_rel floats above it and the staged rows of this launch dense_rel floats above it
+  int64_t flat_rel, dense_rel;
+  int32_t in_place;
   const void* tables;       // device blob
   float* out;               // MODE 0: [rows][n_freq][n_frames]; MODE 1: energies [rows_in_launch][n_filter][n_frames]
   unsigned int* group_max;  // per top_db group maximum energy (float bits), NULL when not needed
@@ -43,6 +47,13 @@ constexpr int kFeMaxDevices = 64;
 int fe_current_device(void);        // cudaGetDevice, -1 on error
 int fe_device_sms(int dev);         // multiprocessor count of `dev`
 
+// A ragged clip the streaming kernel can read where it lies: pad() only truncates it (len >= T), and its first sample
+// is 16-byte aligned relative to the tensor map's base and within reach of a 32-bit TMA coordinate (units of 4 floats).
+// fe_dense_rows_kernel skips exactly these rows; fe_stream_kernel reads exactly these rows from the flat buffer.
+static __host__ __device__ inline bool fe_clip_in_place(int64_t off, int len, int64_t T, int64_t flat_rel) {
+  return flat_rel >= 0 && len >= T && ((off | flat_rel) & 3) == 0 && ((flat_rel + off) >> 2) < 0x7ffffff0LL;
+}
+
 size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch, int mode);
 int fe_fft_pick_ft(int n_fft, int hop, int n_ch, int mode);   // frames per CTA, 0: does not fit shared memory
 cudaError_t fe_launch_fft(const fe_fft_args& a, int mode, int64_t rows, cudaStream_t stream);
@@ -55,7 +66,7 @@ cudaError_t fe_launch_deltas(const float* in, float* out, int64_t rows, int64_t 
 // pre-emphasis, so the streaming kernel (TMA boxes over dense rows) serves those inputs too.  T % 4 == 0.
 cudaError_t fe_launch_dense_rows(const float* wave, const int64_t* offsets, const int32_t* lengths,
                                  int64_t row_base, int64_t rows, int64_t T, float preemph, float* dst,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, int64_t flat_rel = -1);
 // 16-bit PCM -> float32 (x / 32768), n samples; src 8-byte and dst 16-byte aligned.
 cudaError_t fe_launch_i16_rows(const int16_t* src, float* dst, int64_t n, cudaStream_t stream);
 #endif

@@ -67,7 +67,25 @@ struct stream_args {
   int64_t row_base;         // absolute index of the launch's first row (group_max indexing)
   int32_t rows, n_frames, n_filter, hop, nhalf, nstages, kpairs;
   int32_t total_frames, tile_frames, n_tiles, top_db_group;
+  // ragged input read partly in place (offsets != NULL): `wave` is the tensor maps' base, clips that qualify
+  // (fe_clip_in_place) are read from the flat buffer flat_rel floats above it, the others from their staged dense rows
+  // dense_rel floats above it; the maps' last dimension then counts 16-byte units from the base instead of rows
+  const int64_t* offsets;
+  const int32_t* lengths;
+  int64_t flat_rel, dense_rel;
 };
+
+// first sample of launch row `row`, in floats above a.wave
+__device__ __forceinline__ int64_t row_src(const stream_args& a, int row) {
+  if (!a.offsets) return (int64_t)row * a.T;
+  const int64_t arow = a.row_base + row;
+  const int64_t off = __ldg(a.offsets + arow);
+  return fe_clip_in_place(off, __ldg(a.lengths + arow), a.T, a.flat_rel) ? a.flat_rel + off : a.dense_rel + (int64_t)row * a.T;
+}
+// last tensor-map coordinate of a row: the row index over dense rows, 16-byte units above the base for ragged input
+__device__ __forceinline__ int row_coord(const stream_args& a, int row) {
+  return a.offsets ? (int)(row_src(a, row) >> 2) : row;
+}
 
 constexpr int kNumBars = 14;   // BAR_COUNT below
 
@@ -139,9 +157,9 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
 // known before the samples land in shared memory (nothing of it is on the producers' path), and the tile's hop blocks
 // are in L2 when the loader's TMA boxes ask for them.  Edge blocks (v = 0, v = nF: reflect padding) take the same
 // element-wise path the loader uses, so the maxima are those of exactly the samples the producers will see.
-__device__ __forceinline__ void scout_tile_global(const float* wave, int64_t T64, int nF, int hop, const fe_tile_geo& g,
+__device__ __forceinline__ void scout_tile_global(const stream_args& a, int nF, int hop, const fe_tile_geo& g,
                                                   float* s_gmax, int w, int nwarps, int lane) {
-  const int T = (int)T64;
+  const int T = (int)a.T;
   const int r_in = lane >> 3, l8 = lane & 7;
   const int c4 = hop >> 2;                // 16-byte chunks per hop block (hop % 32 == 0: at most 64, 8 per lane)
   for (int r0 = 4 * w; r0 < g.nv; r0 += 4 * nwarps) {
@@ -150,7 +168,7 @@ __device__ __forceinline__ void scout_tile_global(const float* wave, int64_t T64
     if (r < g.nv) {
       const int sv = g.sv0 + r;
       const int row = sv / (nF + 1), v = sv - row * (nF + 1);
-      const float* x = wave + (int64_t)row * T64;
+      const float* x = a.wave + row_src(a, row);
       if (v > 0 && v < nF) {
         const float4* p = reinterpret_cast<const float4*>(x + (int64_t)(v - 1) * hop);
         float4 q[8];
@@ -391,12 +409,12 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         if (lane < 8 && ((cnt >> lane) & 1)) {
           const int first = cnt & ~((2 << lane) - 1);          // blocks taken by the larger boxes
           const int s = row * (nF + 1) + v_lo + first - g.sv0;  // slot of this box's first block
-          tma_box_4d(smem_u32(s_samp + s * rs), &maps.m[lane], bar(BAR_SAMP_FULL), 0, 0, v_lo - 1 + first, row);
+          tma_box_4d(smem_u32(s_samp + s * rs), &maps.m[lane], bar(BAR_SAMP_FULL), 0, 0, v_lo - 1 + first, row_coord(a, row));
         }
       }
       // edge blocks: v = 0 (reflect about sample 0) and v = nF (tail of the utterance + reflect about sample T-1)
       for (int row = g.row0; row <= g.row_last; ++row) {
-        const float* x = a.wave + (int64_t)row * a.T;
+        const float* x = a.wave + row_src(a, row);
         for (int e2 = 0; e2 < 2; ++e2) {
           const int v = e2 ? nF : 0;
           const int s = row * (nF + 1) + v - g.sv0;
@@ -430,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           if (cnt <= 0) continue;
           if (lane < 8 && ((cnt >> lane) & 1)) {
             const int first = cnt & ~((2 << lane) - 1);
-            tma_prefetch_4d(&maps.m[lane], 0, 0, v_lo - 1 + first, row);
+            tma_prefetch_4d(&maps.m[lane], 0, 0, v_lo - 1 + first, row_coord(a, row));
           }
         }
       }
@@ -552,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
       const int tile = blockIdx.x + pre * gridDim.x;
       if (tile < a.n_tiles) {
         const fe_tile_geo g = fe_tile_geometry(tile, a.tile_frames, a.total_frames, nF);
-        scout_tile_global(a.wave, a.T, nF, hop, g, s_gmax + pre * kGmaxStride, warp, kDrainWarps, lane);
+        scout_tile_global(a, nF, hop, g, s_gmax + pre * kGmaxStride, warp, kDrainWarps, lane);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL + pre));
@@ -629,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         const int tile2 = tile + 2 * (int)gridDim.x;
         if (tile2 < a.n_tiles) {
           const fe_tile_geo g2 = fe_tile_geometry(tile2, a.tile_frames, a.total_frames, nF);
-          scout_tile_global(a.wave, a.T, nF, hop, g2, s_gmax + tp * kGmaxStride, warp, kDrainWarps, lane);
+          scout_tile_global(a, nF, hop, g2, s_gmax + tp * kGmaxStride, warp, kDrainWarps, lane);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_SCOUT_FULL + tp));
@@ -707,7 +725,12 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
                              void* gemm_ws, cudaStream_t stream, int* launches) {
   *launches = 0;
   stream_args a;
-  a.wave = fa.wave_chunk ? fa.wave_chunk : fa.wave + row_base * fa.T;
+  const bool in_place = fa.in_place != 0 && fa.wave_chunk && fa.offsets && fa.lengths;
+  a.wave = in_place ? fa.wave : (fa.wave_chunk ? fa.wave_chunk : fa.wave + row_base * fa.T);
+  a.offsets = in_place ? fa.offsets : nullptr;
+  a.lengths = in_place ? fa.lengths : nullptr;
+  a.flat_rel = in_place ? fa.flat_rel : -1;
+  a.dense_rel = in_place ? fa.dense_rel : 0;
   a.tables = fa.tables;
   a.energies = fa.out;
   a.group_max = fa.group_max;
@@ -734,13 +757,14 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
     const void* base;
     int64_t rows, T;
     int32_t hop, n_frames;
-    bool operator==(const map_key& o) const { return base == o.base && rows == o.rows && T == o.T && hop == o.hop && n_frames == o.n_frames; }
+    bool ragged;
+    bool operator==(const map_key& o) const { return base == o.base && rows == o.rows && T == o.T && hop == o.hop && n_frames == o.n_frames && ragged == o.ragged; }
   };
   struct map_entry { map_key key; tmaps8 maps; bool valid; };
   constexpr int kMapCache = 8;
   thread_local map_entry cache[kMapCache];
   thread_local int cache_next = 0;
-  const map_key key{(const void*)a.wave, rows, fa.T, a.hop, fa.n_frames};
+  const map_key key{(const void*)a.wave, rows, fa.T, a.hop, fa.n_frames, in_place};
   const tmaps8* maps_p = nullptr;
   for (int i = 0; i < kMapCache; ++i)
     if (cache[i].valid && cache[i].key == key) { maps_p = &cache[i].maps; break; }
@@ -750,8 +774,9 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
     map_entry& e = cache[cache_next];
     cache_next = (cache_next + 1) % kMapCache;
     e.valid = false;
-    const cuuint64_t gdim[4] = {32, (cuuint64_t)(a.hop / 32), (cuuint64_t)(fa.n_frames - 1), (cuuint64_t)rows};
-    const cuuint64_t gstride[3] = {128, (cuuint64_t)a.hop * 4, (cuuint64_t)fa.T * 4};
+    // ragged input: rows start anywhere (in 16-byte steps) above the base, so the last dimension counts those steps
+    const cuuint64_t gdim[4] = {32, (cuuint64_t)(a.hop / 32), (cuuint64_t)(fa.n_frames - 1), in_place ? (cuuint64_t)0x7fffffff : (cuuint64_t)rows};
+    const cuuint64_t gstride[3] = {128, (cuuint64_t)a.hop * 4, in_place ? (cuuint64_t)16 : (cuuint64_t)fa.T * 4};
     const cuuint32_t estride[4] = {1, 1, 1, 1};
     for (int k = 0; k < 8; ++k) {
       const cuuint32_t box[4] = {32, (cuuint32_t)(a.hop / 32), 1u << k, 1};

@@ -122,7 +122,9 @@ int32_t b200fe_tables_variant(const b200fe_params* p, const void* blob_host);
 int64_t b200fe_workspace_bytes(const b200fe_params* p, int64_t R, int64_t T);
 /* The same for a call that passes offsets / lengths (ragged != 0): with params.variant ==
  * B200FE_VARIANT_DFT_GEMM ragged clips (and pre-emphasised input, ragged or not) are first written as
- * dense repeat-padded rows, one chunk of rows at a time, into the workspace, which grows by chunk*T*4 bytes. */
+ * dense repeat-padded rows, one chunk of rows at a time, into the workspace, which grows by chunk*T*4 bytes
+ * (ragged clips of at least T samples whose first sample is 16-byte aligned are read in place instead; the
+ * workspace size does not depend on how many there are). */
 int64_t b200fe_workspace_bytes_ex(const b200fe_params* p, int64_t R, int64_t T, int32_t ragged);
 
 /* Replaces Spectrogram.forward (transforms/_transforms.py:25; functional.py:119-145, power=2):

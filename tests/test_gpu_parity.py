@@ -209,6 +209,38 @@ def test_ragged_repeat_pad(fe):
         assert_feat_close(a.cpu().numpy(), ref, TOL, f"ragged ({variant}) vs torchaudio on pad()-ed clips")
 
 
+def test_ragged_clips_read_in_place(fe, monkeypatch):
+    """Clips that pad() only truncates (len >= 64600) and that start 16-byte aligned are read by the streaming kernel
+    where they lie; short or unaligned ones are staged as dense rows.  Every mixture equals the dense call bit for
+    bit, and equals the all-staged path (B200FE_STAGE_ALL)."""
+    rs = np.random.RandomState(11)
+    lens = np.array([70000, 64600, 16000, 64604, 99999, 30001, 160000, 64601, 5, 80000, 64600, 123456], dtype=np.int32)
+    clips = [np.clip(0.1 * rs.standard_normal(l), -1, 1).astype(np.float32) for l in lens]
+    dense = cuda(np.stack([O.pad_repeat(c, 64600) for c in clips]))
+    m = fe.LFCCDelta(**LFCC_CFG, variant="dft_gemm")
+    want = m(dense)
+    for align, lead in ((4, 0), (4, 8), (1, 0), (1, 3), (2, 2)):
+        slots = (lens.astype(np.int64) + align - 1) // align * align
+        offsets = lead + np.cumsum(slots) - slots
+        flat = np.zeros(int(lead + slots.sum()), np.float32)
+        for o, c in zip(offsets, clips):
+            flat[o:o + len(c)] = c
+        monkeypatch.delenv("B200FE_STAGE_ALL", raising=False)
+        got = m.forward_ragged(cuda(flat), cuda(offsets), cuda(lens), 64600)
+        assert torch.equal(got, want), (align, lead)
+        monkeypatch.setenv("B200FE_STAGE_ALL", "1")
+        assert torch.equal(m.forward_ragged(cuda(flat), cuda(offsets), cuda(lens), 64600), want), (align, lead)
+        monkeypatch.delenv("B200FE_STAGE_ALL", raising=False)
+    # a batch larger than one tile stream per CTA, all clips long and aligned: nothing is staged
+    n = 300
+    lens2 = rs.randint(64600, 90000, n).astype(np.int32)
+    slots2 = (lens2.astype(np.int64) + 3) // 4 * 4
+    off2 = np.cumsum(slots2) - slots2
+    flat2 = np.clip(0.1 * rs.standard_normal(int(slots2.sum())), -1, 1).astype(np.float32)
+    dense2 = cuda(np.stack([flat2[o:o + 64600] for o in off2]))
+    assert torch.equal(m.forward_ragged(cuda(flat2), cuda(off2), cuda(lens2), 64600), m(dense2))
+
+
 def test_preemphasis_both_variants(fe):
     """Pre-emphasis (torchaudio functional.py:2426) ahead of the LFCC path, applied before the reflect padding."""
     x = synth.s1_noise(6)
