@@ -288,7 +288,7 @@ static int32_t run_features(const float* wave, int64_t R, int64_t T, const int64
         if (offsets && lengths && p->preemph == 0.0f && ((uintptr_t)wave & 15) == 0 && !getenv("B200FE_STAGE_ALL")) {
           const uintptr_t lo = (uintptr_t)wave < (uintptr_t)dense ? (uintptr_t)wave : (uintptr_t)dense;
           const int64_t fr = (int64_t)(((uintptr_t)wave - lo) / 4), dr = (int64_t)(((uintptr_t)dense - lo) / 4);
-          if (((dr + nr * T) >> 2) < 0x7ffffff0LL) {
+          if (((dr + nr * T) >> 2) < kFeInPlaceReach) {
             base = (const float*)lo;
             flat_rel = fr;
             dense_rel = dr;

@@ -48,10 +48,11 @@ int fe_current_device(void);        // cudaGetDevice, -1 on error
 int fe_device_sms(int dev);         // multiprocessor count of `dev`
 
 // A ragged clip the streaming kernel can read where it lies: pad() only truncates it (len >= T), and its first sample
-// is 16-byte aligned relative to the tensor map's base and within reach of a 32-bit TMA coordinate (units of 4 floats).
+// is 16-byte aligned relative to the tensor map's base and within the map's reach (32 steps of 32 GB above the base).
 // fe_dense_rows_kernel skips exactly these rows; fe_stream_kernel reads exactly these rows from the flat buffer.
+constexpr int64_t kFeInPlaceReach = ((int64_t)31 << 31);   // 16-byte units: the 32nd 32 GB step is left as headroom
 static __host__ __device__ inline bool fe_clip_in_place(int64_t off, int len, int64_t T, int64_t flat_rel) {
-  return flat_rel >= 0 && len >= T && ((off | flat_rel) & 3) == 0 && ((flat_rel + off) >> 2) < 0x7ffffff0LL;
+  return flat_rel >= 0 && len >= T && ((off | flat_rel) & 3) == 0 && ((flat_rel + off) >> 2) < kFeInPlaceReach;
 }
 
 size_t fe_fft_smem_bytes(int n_fft, int hop, int ft, int n_ch, int mode);

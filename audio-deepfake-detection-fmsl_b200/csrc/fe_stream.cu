@@ -82,10 +82,6 @@ __device__ __forceinline__ int64_t row_src(const stream_args& a, int row) {
   const int64_t off = __ldg(a.offsets + arow);
   return fe_clip_in_place(off, __ldg(a.lengths + arow), a.T, a.flat_rel) ? a.flat_rel + off : a.dense_rel + (int64_t)row * a.T;
 }
-// last tensor-map coordinate of a row: the row index over dense rows, 16-byte units above the base for ragged input
-__device__ __forceinline__ int row_coord(const stream_args& a, int row) {
-  return a.offsets ? (int)(row_src(a, row) >> 2) : row;
-}
 
 constexpr int kNumBars = 14;   // BAR_COUNT below
 
@@ -146,9 +142,42 @@ __device__ __forceinline__ void tma_box_4d(uint32_t dst, const CUtensorMap* map,
       : "memory");
 }
 
+__device__ __forceinline__ void tma_box_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+               "r"(c4)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
+}
+
+// boxes of 2^k hop blocks starting at block `blk` of launch row `row`.  Dense rows: 4-D maps, last coordinate = row.
+// Ragged input: 5-D maps whose last two dimensions count 16-byte units (2^31 of them = 32 GB) and 32 GB steps above
+// the base, so that the flat clip buffer and the staged rows may lie anywhere in the device's address space.
+__device__ __forceinline__ void row_box(const stream_args& a, uint32_t dst, const CUtensorMap* map, uint32_t bar, int blk, int row) {
+  if (a.offsets) {
+    const int64_t u = row_src(a, row) >> 2;
+    tma_box_5d(dst, map, bar, 0, 0, blk, (int)(u & 0x7fffffff), (int)(u >> 31));
+  } else {
+    tma_box_4d(dst, map, bar, 0, 0, blk, row);
+  }
+}
+__device__ __forceinline__ void row_prefetch(const stream_args& a, const CUtensorMap* map, int blk, int row) {
+  if (a.offsets) {
+    const int64_t u = row_src(a, row) >> 2;
+    tma_prefetch_5d(map, 0, 0, blk, (int)(u & 0x7fffffff), (int)(u >> 31));
+  } else {
+    tma_prefetch_4d(map, 0, 0, blk, row);
+  }
 }
 
 // max |x| of every hop block of a tile, straight from global memory, by `nwarps` warps (this one is `w`): 8 lanes per
@@ -409,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
         if (lane < 8 && ((cnt >> lane) & 1)) {
           const int first = cnt & ~((2 << lane) - 1);          // blocks taken by the larger boxes
           const int s = row * (nF + 1) + v_lo + first - g.sv0;  // slot of this box's first block
-          tma_box_4d(smem_u32(s_samp + s * rs), &maps.m[lane], bar(BAR_SAMP_FULL), 0, 0, v_lo - 1 + first, row_coord(a, row));
+          row_box(a, smem_u32(s_samp + s * rs), &maps.m[lane], bar(BAR_SAMP_FULL), v_lo - 1 + first, row);
         }
       }
       // edge blocks: v = 0 (reflect about sample 0) and v = nF (tail of the utterance + reflect about sample T-1)
@@ -448,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) fe_stream_kernel(const __grid_con
           if (cnt <= 0) continue;
           if (lane < 8 && ((cnt >> lane) & 1)) {
             const int first = cnt & ~((2 << lane) - 1);
-            tma_prefetch_4d(&maps.m[lane], 0, 0, v_lo - 1 + first, row_coord(a, row));
+            row_prefetch(a, &maps.m[lane], v_lo - 1 + first, row);
           }
         }
       }
@@ -774,13 +803,14 @@ cudaError_t fe_stream_launch(const b200fe_params* p, const fe_fft_args& fa, int6
     map_entry& e = cache[cache_next];
     cache_next = (cache_next + 1) % kMapCache;
     e.valid = false;
-    // ragged input: rows start anywhere (in 16-byte steps) above the base, so the last dimension counts those steps
-    const cuuint64_t gdim[4] = {32, (cuuint64_t)(a.hop / 32), (cuuint64_t)(fa.n_frames - 1), in_place ? (cuuint64_t)0x7fffffff : (cuuint64_t)rows};
-    const cuuint64_t gstride[3] = {128, (cuuint64_t)a.hop * 4, in_place ? (cuuint64_t)16 : (cuuint64_t)fa.T * 4};
-    const cuuint32_t estride[4] = {1, 1, 1, 1};
+    // ragged input: rows start anywhere (in 16-byte steps) above the base: the last two dimensions count those steps
+    // (2^31 per 32 GB) and the 32 GB strides (32 of them: 1 TB of reach, beyond any device's memory)
+    const cuuint64_t gdim[5] = {32, (cuuint64_t)(a.hop / 32), (cuuint64_t)(fa.n_frames - 1), in_place ? (cuuint64_t)1 << 31 : (cuuint64_t)rows, 32};
+    const cuuint64_t gstride[4] = {128, (cuuint64_t)a.hop * 4, in_place ? (cuuint64_t)16 : (cuuint64_t)fa.T * 4, (cuuint64_t)1 << 35};
+    const cuuint32_t estride[5] = {1, 1, 1, 1, 1};
     for (int k = 0; k < 8; ++k) {
-      const cuuint32_t box[4] = {32, (cuuint32_t)(a.hop / 32), 1u << k, 1};
-      CUresult r = enc(&e.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.wave, gdim, gstride, box, estride,
+      const cuuint32_t box[5] = {32, (cuuint32_t)(a.hop / 32), 1u << k, 1, 1};
+      CUresult r = enc(&e.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, in_place ? 5 : 4, (void*)a.wave, gdim, gstride, box, estride,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;

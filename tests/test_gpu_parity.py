@@ -241,6 +241,35 @@ def test_ragged_clips_read_in_place(fe, monkeypatch):
     assert torch.equal(m.forward_ragged(cuda(flat2), cuda(off2), cuda(lens2), 64600), m(dense2))
 
 
+def test_ragged_in_place_far_apart_buffers(fe):
+    """The ragged tensor maps reach 32 GB steps above their base: the flat clip buffer and the engine's workspace may
+    lie tens of GB apart.  Both are carved out of one 40 GB allocation here, 39 GB apart, in either order."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 50 << 30:
+        pytest.skip("needs ~45 GB of free device memory")
+    rs = np.random.RandomState(3)
+    lens = np.array([70000, 20000, 64600, 90000, 64603, 100000], dtype=np.int32)
+    slots = (lens.astype(np.int64) + 3) // 4 * 4
+    offsets = np.cumsum(slots) - slots
+    flat = np.clip(0.1 * rs.standard_normal(int(slots.sum())), -1, 1).astype(np.float32)
+    dense = cuda(np.stack([O.pad_repeat(flat[o:o + l], 64600) for o, l in zip(offsets, lens)]))
+    m = fe.LFCCDelta(**LFCC_CFG, variant="dft_gemm")
+    want = m(dense).clone()
+    big = torch.empty(40 << 30, dtype=torch.uint8, device=dev())
+    lo, hi = big[: 64 << 20], big[(39 << 30):]
+    for flat_part, ws_part in ((lo, hi), (hi, lo)):
+        flat_d = flat_part[: flat.nbytes].view(torch.float32)
+        flat_d.copy_(torch.from_numpy(flat))
+        m.engine._workspace.clear()
+        m.engine._workspace[flat_d.device] = ws_part[: 1 << 30] if ws_part is hi else ws_part[32 << 20:]
+        got = m.forward_ragged(flat_d, cuda(offsets), cuda(lens), 64600)
+        ws = m.engine._workspace[flat_d.device]
+        assert abs(ws.data_ptr() - flat_d.data_ptr()) > 32 << 30     # the engine kept the seeded workspace
+        assert torch.equal(got, want)
+    m.engine._workspace.clear()
+    del big
+
+
 def test_preemphasis_both_variants(fe):
     """Pre-emphasis (torchaudio functional.py:2426) ahead of the LFCC path, applied before the reflect padding."""
     x = synth.s1_noise(6)
