@@ -1013,7 +1013,24 @@ __global__ void __launch_bounds__(256) fe_tail_pointwise_kernel(fe_tail_args a) 
 
 cudaError_t set_smem(const void* fn, size_t bytes) {
   if (bytes <= 32 * 1024) return cudaSuccess;   // the 48 KB default covers static + dynamic: opt in well below it
-  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  // The opt-in belongs to (function, device); it costs a microsecond or two per call, which a small-batch launch
+  // notices.  Each host thread remembers the largest size it has been granted per (function, device).
+  struct granted { const void* fn; int dev; size_t bytes; };
+  constexpr int kSlots = 16;
+  thread_local granted cache[kSlots] = {};
+  thread_local int next = 0;
+  const int dev = fe_current_device();
+  for (int i = 0; i < kSlots; ++i)
+    if (cache[i].fn == fn && cache[i].dev == dev && cache[i].bytes >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0) {
+    int at = -1;
+    for (int i = 0; i < kSlots; ++i)
+      if (cache[i].fn == fn && cache[i].dev == dev) at = i;
+    if (at < 0) { at = next; next = (next + 1) % kSlots; }
+    cache[at] = granted{fn, dev, bytes};
+  }
+  return e;
 }
 
 }  // namespace
