@@ -11,7 +11,7 @@ alias module at the repository root.
 """
 from . import _lib
 from .transforms import (ComputeDeltas, FrontEndEngine, LFCC, LFCCDelta, MelSpectrogram, Spectrogram,
-                         create_dct, linear_fbanks, melscale_fbanks)
+                         create_dct, linear_fbanks, melscale_fbanks, pack_clips)
 from .maze import LFCC_FILTS, FeatureSlot, MazeScorer, fill_deterministic
 from .evaluation import eer_min_dcf, eer_min_dcf_device, gather_scores, shard_range, write_score_file
 
@@ -25,7 +25,7 @@ B200ComputeDeltas = ComputeDeltas
 __all__ = [
     "LFCC", "LFCCDelta", "MelSpectrogram", "Spectrogram", "ComputeDeltas", "FrontEndEngine",
     "B200LFCC", "B200LFCCDelta", "B200MelSpectrogram", "B200Spectrogram", "B200ComputeDeltas",
-    "linear_fbanks", "melscale_fbanks", "create_dct",
+    "linear_fbanks", "melscale_fbanks", "create_dct", "pack_clips",
     "MazeScorer", "FeatureSlot", "LFCC_FILTS", "fill_deterministic",
     "shard_range", "gather_scores", "eer_min_dcf", "eer_min_dcf_device", "write_score_file",
 ]

@@ -367,6 +367,28 @@ def _pack_rows(waveform: Tensor) -> Tuple[Tensor, Tuple[int, ...]]:
     return w, shape
 
 
+def pack_clips(clips, align: int = 4, pin_memory: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    """Variable-length clips (1-D float32 tensors or arrays, as the reference's loader reads them before ``pad()``,
+    maze5.py:280-351) -> the ragged input of ``forward_ragged``: ``(flat, offsets int64, lengths int32)`` on the
+    host.  Every clip starts on a multiple of ``align`` samples (default 4 = 16 bytes, up to 3 zero samples of slack
+    between clips): clips that ``pad()`` only truncates are then read by the streaming kernel where they lie instead
+    of being staged as dense rows.  An empty clip raises, as ``pad()`` does."""
+    if align < 1:
+        raise ValueError("align must be >= 1")
+    ts = [torch.as_tensor(c, dtype=torch.float32).reshape(-1) for c in clips]
+    if not ts:
+        raise ValueError("no clips")
+    lengths = torch.tensor([t.numel() for t in ts], dtype=torch.int64)
+    if int(lengths.min()) < 1:
+        raise ValueError("every clip must have at least one sample")
+    slots = (lengths + align - 1) // align * align
+    offsets = torch.cumsum(slots, 0) - slots
+    flat = torch.zeros(int(slots.sum()), dtype=torch.float32, pin_memory=pin_memory)
+    for t, o in zip(ts, offsets.tolist()):
+        flat[o:o + t.numel()] = t
+    return flat, offsets, lengths.to(torch.int32)
+
+
 def _torchaudio_group(shape: Tuple[int, ...]) -> int:
     """Rows sharing one ``top_db`` maximum in torchaudio's ``amplitude_to_DB`` for a waveform of this
     shape (functional/functional.py:394-399): the spectrogram has one more dimension than the

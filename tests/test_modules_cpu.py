@@ -103,3 +103,23 @@ def test_missing_library_fails_loudly(fe, monkeypatch):
     monkeypatch.setattr(fe._lib, "LIB_PATH", "/nonexistent/libb200fe.so")
     with pytest.raises(OSError, match="no CPU fallback"):
         fe._lib.load()
+
+
+def test_pack_clips_aligns_clip_starts(fe):
+    """pack_clips: the ragged input with every clip on a 16-byte boundary (what lets the streaming kernel read the
+    clips that pad() only truncates in place), clips recoverable bit for bit, empty clips refused like pad()."""
+    rs = np.random.RandomState(0)
+    clips = [rs.standard_normal(n).astype(np.float32) for n in (5, 64600, 1, 70001, 16000)]
+    flat, offsets, lengths = fe.pack_clips(clips)
+    assert flat.dtype == torch.float32 and offsets.dtype == torch.int64 and lengths.dtype == torch.int32
+    assert lengths.tolist() == [5, 64600, 1, 70001, 16000]
+    assert all(o % 4 == 0 for o in offsets.tolist())
+    assert offsets.tolist() == [0, 8, 64608, 64612, 134616] and flat.numel() == 150616
+    for c, o, l in zip(clips, offsets.tolist(), lengths.tolist()):
+        assert np.array_equal(flat[o:o + l].numpy(), c)
+    f1, o1, _ = fe.pack_clips([torch.from_numpy(c) for c in clips], align=1)     # back to back
+    assert o1.tolist() == [0, 5, 64605, 64606, 134607] and f1.numel() == 150607
+    with pytest.raises(ValueError):
+        fe.pack_clips([clips[0], np.zeros(0, np.float32)])
+    with pytest.raises(ValueError):
+        fe.pack_clips([])
