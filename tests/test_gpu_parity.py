@@ -231,6 +231,8 @@ def test_ragged_clips_read_in_place(fe, monkeypatch):
         monkeypatch.setenv("B200FE_STAGE_ALL", "1")
         assert torch.equal(m.forward_ragged(cuda(flat), cuda(offsets), cuda(lens), 64600), want), (align, lead)
         monkeypatch.delenv("B200FE_STAGE_ALL", raising=False)
+    flat_p, off_p, len_p = fe.pack_clips(clips)      # the packer of the package: 16-byte aligned clip starts
+    assert torch.equal(m.forward_ragged(flat_p.to(dev()), off_p.to(dev()), len_p.to(dev()), 64600), want)
     # a batch larger than one tile stream per CTA, all clips long and aligned: nothing is staged
     n = 300
     lens2 = rs.randint(64600, 90000, n).astype(np.int32)
