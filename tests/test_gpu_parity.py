@@ -243,6 +243,36 @@ def test_ragged_clips_read_in_place(fe, monkeypatch):
     assert torch.equal(m.forward_ragged(cuda(flat2), cuda(off2), cuda(lens2), 64600), m(dense2))
 
 
+def test_ragged_in_place_across_chunks():
+    """Two chunks of rows (B200FE_WS_MB=8, read once per process -> a subprocess): the in-place rows of the second
+    chunk are addressed by their absolute row index (offsets / lengths), the staged ones by their index in the chunk."""
+    import os
+    import subprocess
+    import sys
+    script = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import b200_frontend as fe
+from helpers import LFCC_CFG
+from oracle import frontend_oracle as O
+rs = np.random.RandomState(7)
+lens = rs.randint(30000, 100000, 300).astype(np.int32)
+clips = [np.clip(0.1 * rs.standard_normal(l), -1, 1).astype(np.float32) for l in lens]
+flat, off, ln = fe.pack_clips(clips)
+dense = torch.from_numpy(np.stack([O.pad_repeat(c, 64600) for c in clips])).cuda()
+m = fe.LFCCDelta(**LFCC_CFG, variant="dft_gemm")
+a = m.forward_ragged(flat.cuda(), off.cuda(), ln.cuda(), 64600)
+assert m.engine.last_launch_count() >= 6, m.engine.last_launch_count()     # two chunks of (dense rows, stream, tail)
+b = m(dense)
+assert torch.equal(a, b)
+print("chunks-ok")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200FE_WS_MB="8")
+    r = subprocess.run([sys.executable, "-c", script], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "chunks-ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_ragged_in_place_far_apart_buffers(fe):
     """The ragged tensor maps reach 32 GB steps above their base: the flat clip buffer and the engine's workspace may
     lie tens of GB apart.  Both are carved out of one 40 GB allocation here, 39 GB apart, in either order."""
