@@ -1301,10 +1301,13 @@ cudaError_t fe_launch_deltas(const float* in, float* out, int64_t rows, int64_t 
 cudaError_t fe_launch_dense_rows(const float* wave, const int64_t* offsets, const int32_t* lengths,
                                  int64_t row_base, int64_t rows, int64_t T, float preemph, float* dst,
                                  cudaStream_t stream, int64_t flat_rel) {
-  // rows the streaming kernel reads in place leave at once: with them in the batch, 8 CTAs per row (each thread walks
-  // the row in 8 steps) instead of one CTA per 1024 samples, so that a skipped row costs 8 empty CTAs, not 64
+  // CTAs per row: each thread walks its row in T / (1024 bx) steps.  One CTA per 1024 samples (64 per LFCC row) was
+  // measured slowest; 16 per row is best when every row is copied (all-staged ragged step 1.30 -> 1.24 ms per 4096
+  // clips, profiles/r2_ragged_inplace.txt), 8 when rows the streaming kernel reads in place are in the batch: those
+  // leave at once, and a skipped row should cost few empty CTAs.
   unsigned bx = (unsigned)((T / 4 + 255) / 256);
-  if (flat_rel >= 0 && bx > 8) bx = 8;
+  const unsigned cap = flat_rel >= 0 ? 8 : 16;
+  if (bx > cap) bx = cap;
   for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
     const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
     dim3 grid(bx, (unsigned)nr);
